@@ -1,0 +1,125 @@
+// common.cuh -- shared declarations for the nerfb200 CUDA library (sm_100a).
+//
+// The "plan" is the host-built description of one FlexibleNeRFModel (nerf/models.py:185-256 of the
+// reference) as a chain of GEMM layers (outputs of 64*NJ columns, evaluated tile-by-tile) and up
+// to two narrow "heads" (fc_alpha: 1 output, fc_rgb: 3, fc_out: 4) that are evaluated as dot
+// products.  It is passed by value to every kernel.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/nerfb200.h"
+
+namespace nerfb200 {
+
+constexpr int kMaxGemm = 20;
+constexpr int kTileRows = 128;   // points per CTA tile
+constexpr int kThreads = 256;    // threads per CTA in the MLP kernels
+
+struct GemmLayer {
+  int k_h;       // input columns taken from the previous activation (0 for layer1, else hidden)
+  int k_enc;     // padded (multiple of 8) encoded-input columns appended after k_h (0 if none)
+  int enc_real;  // real encoded columns (63 / 27 / ...)
+  int enc_sel;   // 0: xyz encoding, 1: direction encoding
+  int n;         // output features (hidden or hidden/2), multiple of 64
+  int relu;      // ReLU after the bias (layer1 has none: models.py:238)
+  int wt_off;    // blob offset of Wt[k_h + k_enc][n]   (forward operand)
+  int wh_off;    // blob offset of Wh[n][k_h]           (dgrad operand; h-part only)
+  int b_off;     // blob offset of bias[n]
+  int cum_n;     // sum of n over previous gemm layers: stash slice = base + n_points * cum_n
+  int flat_w;    // offset of weight[n][k_h + enc_real] in the flat (torch-layout) vector
+  int flat_b;    // offset of bias[n] in the flat vector
+  int src;       // gemm index whose output is this layer's h-input (-1 for layer1)
+};
+
+struct HeadLayer {
+  int k;        // input features
+  int n_out;    // 1, 3 or 4
+  int out_col;  // first column of raw[...,4] it produces
+  int w_off;    // blob offset of W[n_out][k] (torch layout), 4-float aligned
+  int b_off;    // blob offset of bias[4]
+  int src;      // gemm index whose output it reads
+  int flat_w, flat_b;
+};
+
+struct Plan {
+  int n_gemm;
+  int n_trunk;  // gemm layers 0..n_trunk-1 are layer1 + layers_xyz
+  int n_head;
+  int hidden;
+  int sum_n;  // sum of n over all gemm layers = floats stashed per point
+  int dim_xyz, dim_xyz_pad, dim_dir, dim_dir_pad;
+  int n_freq_xyz, n_freq_dir, inc_xyz, inc_dir;
+  int blob_floats, flat_floats;
+  int use_viewdirs;
+  GemmLayer g[kMaxGemm];
+  HeadLayer h[2];  // viewdirs: h[0] = fc_alpha (after trunk), h[1] = fc_rgb (after dir layer); else h[0] = fc_out
+  float freq_xyz[NERFB200_MAX_FREQS];
+  float freq_dir[NERFB200_MAX_FREQS];
+};
+
+// host side (api.cu)
+int build_plan(const nerfb200_arch_t* arch, Plan* plan);  // 0 or NERFB200_ERR_*
+void set_error(const char* fmt, ...);
+int check_cuda(cudaError_t e, const char* what);
+
+// launchers (one per .cu), all return NERFB200_OK or an error code
+int launch_pack(const Plan& p, const float* flat, float* blob, cudaStream_t s);
+int launch_sample_coarse(const float* rays, int ray_stride, int64_t n_rays, const float* t_vals,
+                         const float* t_rand, int n_coarse, int perturb, int lindisp, float* z, cudaStream_t s);
+int launch_encode(const Plan& p, int which, const float* x, int64_t n, float* out, cudaStream_t s);
+int launch_mlp_fwd_simt(const Plan& p, const float* blob, const float* rays, int ray_stride, const float* z,
+                        int64_t n_rays, int n_samples, float* raw, float* stash, cudaStream_t s);
+int launch_mlp_bwd_simt(const Plan& p, const float* blob, const float* rays, int ray_stride, const float* z,
+                        int64_t n_rays, int n_samples, const float* d_raw, const float* stash, float* gstash,
+                        float* flat_grad, cudaStream_t s);
+int launch_composite_fwd(const float* raw, const float* z, const float* rays, int ray_stride, const float* noise,
+                         int64_t n_rays, int n_samples, float noise_std, int white_bkgd, float* out,
+                         float* weights, cudaStream_t s);
+int launch_composite_bwd(const float* raw, const float* z, const float* rays, int ray_stride, const float* noise,
+                         const float* g_out, int64_t n_rays, int n_samples, float noise_std, int white_bkgd,
+                         float* d_raw, cudaStream_t s);
+int launch_sample_pdf_merge(const float* z_coarse, const float* weights_coarse, const float* u, int u_stride,
+                            const float* cdf_in, int64_t n_rays, int n_coarse, int n_fine, float* z_fine,
+                            float* z_samples, int32_t* inds, float* cdf_out, cudaStream_t s);
+int launch_adam(float* p, const float* g, float* m, float* v, int64_t n, int step, float lr, float b1, float b2,
+                float eps, float grad_scale, cudaStream_t s);
+// tcgen05 path (mlp_tc.cu)
+int launch_mlp_fwd_tc(const Plan& p, const float* blob, const float* rays, int ray_stride, const float* z,
+                      int64_t n_rays, int n_samples, float* raw, float* stash, cudaStream_t s);
+
+// ---------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+// Positional encoding of one scalar coordinate (nerf_helpers.py:113-157): writes x (if include) and
+// sin/cos(x * f_i) at the reference's channel positions for coordinate c of 3:
+//   [x y z | sin(f0 xyz) | cos(f0 xyz) | sin(f1 xyz) | ...]
+// `row` points at the start of this point's encoding.  x * f is rounded to fp32 first, as the
+// reference evaluates `tensor * freq` before sin/cos (nerf_helpers.py:149-151).
+__device__ __forceinline__ void encode_coord(float x, int c, int include, int f_begin, int f_end,
+                                             const float* __restrict__ freqs, float* __restrict__ row) {
+  const int base = include ? 3 : 0;
+  if (include && f_begin == 0) row[c] = x;
+  for (int f = f_begin; f < f_end; ++f) {
+    float s, co;
+    sincosf(__fmul_rn(x, freqs[f]), &s, &co);
+    row[base + 6 * f + c] = s;
+    row[base + 6 * f + 3 + c] = co;
+  }
+}
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  unsigned sa = static_cast<unsigned>(__cvta_generic_to_shared(smem));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+#endif  // __CUDACC__
+
+}  // namespace nerfb200

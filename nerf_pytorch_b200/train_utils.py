@@ -1,0 +1,353 @@
+"""Drop-in replacements for the reference's render driver (nerf/train_utils.py):
+
+    run_one_iter_of_nerf            nerf/train_utils.py:130-202
+    predict_and_render_radiance     nerf/train_utils.py:28-127
+
+Same positional signatures, same option keys (``options.nerf.<mode>.*``, ``options.dataset.*``),
+same 6-tuple result, differentiable w.r.t. the parameters of both models.  Everything per-ray
+(stratified sampling, encoding, both MLPs, compositing, hierarchical resampling, their backward)
+runs in libnerfb200.so; this file only moves pointers: it reads the options, draws the random
+tensors in the reference's order (so a shared torch seed gives the reference-on-GPU's random
+stream), flattens the parameters and calls the C ABI through ``ops``.
+
+There is no PyTorch fallback: an unsupported model / device / dtype raises.
+"""
+from __future__ import annotations
+
+import weakref
+from typing import Optional
+
+import torch
+
+from . import ops
+from .nerf_helpers import Embedder, get_minibatches, ndc_rays
+
+# The reference does not forward ``mode`` to predict_and_render_radiance (train_utils.py:171-181),
+# so validation renders use options.nerf.train.* for sampling/noise.  True reproduces that.
+COMPAT_MODE_QUIRK = True
+
+# 0: fp32 CUDA cores (default, bit-faithful fp32 arithmetic); 1: tcgen05 tensor cores (3xTF32)
+DEFAULT_IMPL = ops.IMPL_SIMT
+
+# gradient synchronisation across ranks: (process_group, world_size) or None; see parallel.py
+_GRAD_SYNC = None
+
+
+def set_default_impl(impl: int):
+    global DEFAULT_IMPL
+    DEFAULT_IMPL = int(impl)
+
+
+# --------------------------------------------------------------------------------------------------
+# model / encoder introspection
+# --------------------------------------------------------------------------------------------------
+def _probe_encoder(fn, dim_expected: Optional[int]):
+    """(L, include_input, log_sampling) of an encoder.  ``Embedder`` objects carry their parameters;
+    an opaque callable (the reference's own lambda, nerf_helpers.py:160-167) is identified by
+    evaluating it once on a CPU probe and matching the stock encoding."""
+    if fn is None:
+        return None
+    if isinstance(fn, Embedder) or all(hasattr(fn, a) for a in ("num_encoding_functions", "include_input", "log_sampling")):
+        return int(fn.num_encoding_functions), bool(fn.include_input), bool(fn.log_sampling)
+    probe = torch.tensor([[0.3, -0.7, 1.1]], dtype=torch.float32)
+    try:
+        got = fn(probe)
+    except Exception as e:  # pragma: no cover - user callables
+        raise NotImplementedError(f"nerfb200: cannot introspect encoder {fn!r}: {e}")
+    dim = got.shape[-1]
+    for include in (True, False):
+        rest = dim - (3 if include else 0)
+        if rest < 0 or rest % 6:
+            continue
+        L = rest // 6
+        for log_sampling in (True, False):
+            bands = ops.frequency_bands(L, log_sampling)
+            parts = [probe] if include else []
+            for f in bands:
+                parts += [torch.sin(probe * f), torch.cos(probe * f)]
+            ref = torch.cat(parts, -1) if len(parts) > 1 else parts[0]
+            if ref.shape == got.shape and torch.allclose(ref, got.cpu().float(), atol=1e-6):
+                return L, include, log_sampling
+    raise NotImplementedError("nerfb200: encoder is not the stock positional_encoding; no fused path for it")
+
+
+def _arch_of(model, enc_xyz, enc_dir) -> ops.ArchSpec:
+    need = ("layer1", "layers_xyz")
+    if not all(hasattr(model, a) for a in need):
+        raise NotImplementedError(
+            f"nerfb200: {type(model).__name__} is not a FlexibleNeRFModel (nerf/models.py:185); only that family is fused")
+    use_viewdirs = hasattr(model, "fc_rgb")
+    hidden = model.layer1.out_features
+    n_xyz = len(model.layers_xyz)
+    wide = [i for i, l in enumerate(model.layers_xyz) if l.in_features != l.out_features]
+    skip = int(getattr(model, "skip_connect_every", 0)) or (wide[0] if wide else n_xyz + 1)
+    rule = [i for i in range(n_xyz) if i % skip == 0 and i > 0]
+    if rule != wide:
+        raise NotImplementedError(f"nerfb200: skip layers {wide} do not follow skip_connect_every={skip}")
+    Lx, incx, logx = enc_xyz
+    if use_viewdirs:
+        if enc_dir is None:
+            raise RuntimeError("nerfb200: model uses view directions but no direction encoder was given")
+        Ld, incd, logd = enc_dir
+    else:
+        Ld, incd, logd = 0, True, True
+    arch = ops.ArchSpec(num_layers=n_xyz + 1, hidden=hidden, skip_every=skip, use_viewdirs=use_viewdirs,
+                        n_freq_xyz=Lx, n_freq_dir=Ld, include_input_xyz=incx, include_input_dir=incd,
+                        log_sampling_xyz=logx, log_sampling_dir=logd)
+    if model.layer1.in_features != arch.dim_xyz:
+        raise RuntimeError(f"nerfb200: layer1 expects {model.layer1.in_features} inputs, encoder produces {arch.dim_xyz}")
+    if use_viewdirs and model.layers_dir[0].in_features != hidden + arch.dim_dir:
+        raise RuntimeError("nerfb200: layers_dir[0] width does not match the direction encoder")
+    return arch
+
+
+def _ordered_params(model, arch: ops.ArchSpec):
+    mods = [model.layer1] + list(model.layers_xyz)
+    if arch.use_viewdirs:
+        mods += [model.fc_feat, model.fc_alpha, model.layers_dir[0], model.fc_rgb]
+    else:
+        mods += [model.fc_out]
+    out = []
+    for m in mods:
+        out += [m.weight, m.bias]
+    return out
+
+
+class _Packed:
+    """Per-model cache: flat parameter vector + kernel blob, refreshed when any parameter changes
+    (torch bumps ``_version`` on every in-place optimizer update)."""
+
+    __slots__ = ("arch", "key", "flat", "blob")
+
+    def __init__(self):
+        self.arch = None
+        self.key = None
+        self.flat = None
+        self.blob = None
+
+
+_CACHE: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
+
+
+def _flat_view_if_contiguous(params):
+    """If the parameters already live back-to-back in one storage (parallel.flatten_parameters),
+    return that storage slice without copying."""
+    p0 = params[0]
+    base = p0.data_ptr()
+    off = 0
+    for p in params:
+        if p.data_ptr() != base + 4 * off or not p.is_contiguous():
+            return None
+        off += p.numel()
+    flat = getattr(p0, "_nerfb200_flat", None)
+    if flat is not None and flat.data_ptr() == base and flat.numel() == off:
+        return flat
+    return None
+
+
+def _packed(model, arch: ops.ArchSpec):
+    params = _ordered_params(model, arch)
+    for p in params:
+        if not p.is_cuda or p.dtype != torch.float32:
+            raise NotImplementedError("nerfb200: parameters must be fp32 CUDA tensors (no CPU / half path)")
+    ent = _CACHE.get(model)
+    if ent is None:
+        ent = _CACHE[model] = _Packed()
+    key = (arch, tuple(p._version for p in params), tuple(p.data_ptr() for p in params),
+           getattr(model, "_nerfb200_epoch", 0))
+    if ent.key != key:
+        with torch.no_grad():
+            flat = _flat_view_if_contiguous(params)
+            if flat is None:
+                flat = torch.cat([p.detach().reshape(-1) for p in params])
+            ent.flat = flat
+            ent.blob = ops.pack_weights(arch, flat, None)  # fresh blob: an in-flight backward may still hold the old one
+        ent.arch, ent.key = arch, key
+    return params, ent.blob
+
+
+# --------------------------------------------------------------------------------------------------
+# autograd bridge for one ray chunk
+# --------------------------------------------------------------------------------------------------
+class _RenderChunk(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, cfg, rays, t_vals, t_rand, noise_c, u, noise_f, *params):
+        arch_c, arch_f, opts, blob_c, blob_f, training, impl, n_pc = cfg
+        out_c, out_f, ws = ops.render_fwd(arch_c, arch_f, opts, blob_c, blob_f, rays, t_vals, t_rand, noise_c, u,
+                                          noise_f, training=training, impl=impl)
+        if training:
+            ctx.cfg = cfg
+            ctx.ws = ws
+            ctx.save_for_backward(rays, noise_c, noise_f)
+        ctx.set_materialize_grads(False)
+        if out_f is None:
+            return out_c, None
+        return out_c, out_f
+
+    @staticmethod
+    def backward(ctx, g_c, g_f):
+        arch_c, arch_f, opts, blob_c, blob_f, training, impl, n_pc = ctx.cfg
+        rays, noise_c, noise_f = ctx.saved_tensors
+        fine = opts.n_fine > 0
+        n = rays.shape[0]
+        if g_c is None:
+            g_c = torch.zeros(n, 8, dtype=torch.float32, device=rays.device)
+        if fine and g_f is None:
+            g_f = torch.zeros(n, 8, dtype=torch.float32, device=rays.device)
+        nc = arch_c.flat_param_count()
+        nf = arch_f.flat_param_count() if fine else 0
+        flat_grad = torch.zeros(nc + nf, dtype=torch.float32, device=rays.device)
+        ops.render_bwd(arch_c, arch_f, opts, blob_c, blob_f, rays, noise_c, noise_f, g_c.contiguous(),
+                       g_f.contiguous() if fine else None, ctx.ws, flat_grad[:nc], flat_grad[nc:] if fine else None,
+                       impl=impl)
+        ctx.ws = None
+        if _GRAD_SYNC is not None:
+            # the ONE collective of a data-parallel step: both nets' gradients in one flat buffer
+            import torch.distributed as dist
+
+            group, world = _GRAD_SYNC
+            dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=group)
+            flat_grad.mul_(1.0 / world)
+        grads = []
+        for arch, base in ((arch_c, 0),) + (((arch_f, nc),) if fine else ()):
+            for _, w_off, b_off, fin, fout in arch.flat_layout():
+                grads.append(flat_grad[base + w_off: base + w_off + fin * fout].view(fout, fin))
+                grads.append(flat_grad[base + b_off: base + b_off + fout])
+        return (None,) * 7 + tuple(grads)
+
+
+# --------------------------------------------------------------------------------------------------
+# public API
+# --------------------------------------------------------------------------------------------------
+def predict_and_render_radiance(
+    ray_batch,
+    model_coarse,
+    model_fine,
+    options,
+    mode="train",
+    encode_position_fn=None,
+    encode_direction_fn=None,
+    *,
+    randoms: Optional[dict] = None,
+    impl: Optional[int] = None,
+):
+    """nerf/train_utils.py:28-127 for one chunk of packed rays ``[o d near far (viewdir)]``.
+
+    ``randoms`` (keyword-only, optional) injects the four random tensors the reference would draw
+    (t_rand, noise_c, u, noise_f); by default they are drawn here with torch.rand/randn in the
+    reference's order."""
+    o = getattr(options.nerf, mode)
+    if not ray_batch.is_cuda:
+        raise NotImplementedError("nerfb200: rays must be on a CUDA device (there is no CPU path)")
+    rays = ray_batch.detach().float().contiguous()
+    n, dev = rays.shape[0], rays.device
+    enc_xyz = _probe_encoder(encode_position_fn, None)
+    if enc_xyz is None:
+        raise RuntimeError("nerfb200: encode_position_fn is required (the reference crashes without it too)")
+    enc_dir = _probe_encoder(encode_direction_fn, None)
+    nc, nf = int(o.num_coarse), int(o.num_fine)
+    fine = nf > 0
+    if fine and not model_fine:
+        raise RuntimeError("nerfb200: num_fine > 0 but model_fine is None (the reference fails here as well)")
+    arch_c = _arch_of(model_coarse, enc_xyz, enc_dir)
+    arch_f = _arch_of(model_fine, enc_xyz, enc_dir) if fine else None
+    params_c, blob_c = _packed(model_coarse, arch_c)
+    params_f, blob_f = _packed(model_fine, arch_f) if fine else ([], None)
+    noise_std = float(o.radiance_field_noise_std)
+    perturb = bool(o.perturb)
+    opts = ops.make_opts(nc, nf, perturb, o.lindisp, o.white_background, noise_std)
+
+    rnd = randoms or {}
+
+    def take(name, shape, fn):
+        t = rnd.get(name)
+        if t is None:
+            return fn(shape, dtype=torch.float32, device=dev)
+        return t.to(device=dev, dtype=torch.float32).contiguous()
+
+    # reference draw order: rand(N,Nc) -> randn(N,Nc) -> rand(N,Nf) -> randn(N,Nc+Nf)  
+    t_vals = torch.linspace(0.0, 1.0, nc, dtype=torch.float32, device=dev)
+    t_rand = take("t_rand", (n, nc), torch.rand) if perturb else None
+    noise_c = take("noise_c", (n, nc), torch.randn) if noise_std > 0.0 else None
+    u = noise_f = None
+    if fine:
+        if perturb:
+            u = take("u", (n, nf), torch.rand)
+        else:  # det = (perturb == 0.0): shared linspace, nerf_helpers.py:272-276
+            u = torch.linspace(0.0, 1.0, steps=nf, dtype=torch.float32, device=dev)
+        noise_f = take("noise_f", (n, nc + nf), torch.randn) if noise_std > 0.0 else None
+
+    all_params = list(params_c) + list(params_f)
+    training = torch.is_grad_enabled() and any(p.requires_grad for p in all_params)
+    cfg = (arch_c, arch_f, opts, blob_c, blob_f, training, DEFAULT_IMPL if impl is None else int(impl), len(params_c))
+    out_c, out_f = _RenderChunk.apply(cfg, rays, t_vals, t_rand, noise_c, u, noise_f, *all_params)
+    rgb_c, disp_c, acc_c = out_c[:, :3], out_c[:, 3], out_c[:, 4]
+    if out_f is None:
+        return rgb_c, disp_c, acc_c, None, None, None
+    return rgb_c, disp_c, acc_c, out_f[:, :3], out_f[:, 3], out_f[:, 4]
+
+
+def run_one_iter_of_nerf(
+    height,
+    width,
+    focal_length,
+    model_coarse,
+    model_fine,
+    ray_origins,
+    ray_directions,
+    options,
+    mode="train",
+    encode_position_fn=None,
+    encode_direction_fn=None,
+    *,
+    randoms: Optional[dict] = None,
+    impl: Optional[int] = None,
+):
+    """nerf/train_utils.py:130-202: ray packing (viewdirs, optional NDC, near/far), chunking by
+    ``options.nerf.<mode>.chunksize``, per-chunk render, concatenation and -- in "validation" mode --
+    the reshape back to image shape."""
+    viewdirs = None
+    if options.nerf.use_viewdirs:
+        viewdirs = ray_directions
+        viewdirs = viewdirs / viewdirs.norm(p=2, dim=-1).unsqueeze(-1)
+        viewdirs = viewdirs.view((-1, 3))
+    restore_shapes = [ray_directions.shape, ray_directions.shape[:-1], ray_directions.shape[:-1]]
+    if model_fine:
+        restore_shapes += restore_shapes
+    if options.dataset.no_ndc is False:
+        ro, rd = ndc_rays(height, width, focal_length, 1.0, ray_origins, ray_directions)
+        ro, rd = ro.view((-1, 3)), rd.view((-1, 3))
+    else:
+        ro, rd = ray_origins.view((-1, 3)), ray_directions.view((-1, 3))
+    near = options.dataset.near * torch.ones_like(rd[..., :1])
+    far = options.dataset.far * torch.ones_like(rd[..., :1])
+    rays = torch.cat((ro, rd, near, far), dim=-1)
+    if options.nerf.use_viewdirs:
+        rays = torch.cat((rays, viewdirs), dim=-1)
+
+    batches = get_minibatches(rays, chunksize=getattr(options.nerf, mode).chunksize)
+    if randoms is not None and len(batches) != 1:
+        raise ValueError("injected randoms require a single ray chunk")
+    inner_mode = "train" if COMPAT_MODE_QUIRK else mode
+    pred = [
+        predict_and_render_radiance(
+            batch, model_coarse, model_fine, options, mode=inner_mode,
+            encode_position_fn=encode_position_fn,
+            encode_direction_fn=encode_direction_fn if options.nerf.use_viewdirs else None,
+            randoms=randoms, impl=impl,
+        )
+        for batch in batches
+    ]
+    synthesized_images = list(zip(*pred))
+    synthesized_images = [
+        torch.cat(image, dim=0) if image[0] is not None else None for image in synthesized_images
+    ]
+    if mode == "validation":
+        synthesized_images = [
+            image.view(shape) if image is not None else None
+            for (image, shape) in zip(synthesized_images, restore_shapes)
+        ]
+        if model_fine:
+            return tuple(synthesized_images)
+        return tuple(synthesized_images + [None, None, None])
+    return tuple(synthesized_images)

@@ -247,9 +247,9 @@ def predict_and_render_radiance(
     enc_dir = _probe_encoder(encode_direction_fn, None)
     nc, nf = int(o.num_coarse), int(o.num_fine)
     fine = nf > 0
+    arch_c = _arch_of(model_coarse, enc_xyz, enc_dir)
     if fine and not model_fine:
         raise RuntimeError("nerfb200: num_fine > 0 but model_fine is None (the reference fails here as well)")
-    arch_c = _arch_of(model_coarse, enc_xyz, enc_dir)
     arch_f = _arch_of(model_fine, enc_xyz, enc_dir) if fine else None
     params_c, blob_c = _packed(model_coarse, arch_c)
     params_f, blob_f = _packed(model_fine, arch_f) if fine else ([], None)

@@ -63,6 +63,8 @@ typedef struct nerfb200_render_opts {
 
 int32_t nerfb200_version(void);
 const char* nerfb200_last_error(void);
+/* number of CUDA kernels this library has launched in this process (all threads) */
+int64_t nerfb200_launch_count(void);
 
 /* ---- parameters -------------------------------------------------------------------------------
  * Canonical order of the linears ("slots"): layer1, layers_xyz[0..num_layers-2], then

@@ -4,12 +4,14 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <atomic>
 
 #include "common.cuh"
 
 namespace nerfb200 {
 
 static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -17,6 +19,8 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 int check_cuda(cudaError_t e, const char* what) {
   if (e == cudaSuccess) return NERFB200_OK;
@@ -86,6 +90,9 @@ int build_plan(const nerfb200_arch_t* a, Plan* p) {
     blob += n * g.k_h;
     g.b_off = blob;
     blob += n;
+    g.k_tc = enc_sel == 1 ? k_h : k_h + g.k_enc;
+    g.tc_off = blob;
+    blob += 2 * g.k_tc * n;  // hi + lo copies
     g.cum_n = cum;
     cum += n;
     g.flat_w = flat;
@@ -226,6 +233,7 @@ extern "C" {
 
 int32_t nerfb200_version(void) { return NERFB200_VERSION; }
 const char* nerfb200_last_error(void) { return g_err; }
+int64_t nerfb200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 int64_t nerfb200_num_linear(const nerfb200_arch_t* arch) {
   Plan p;

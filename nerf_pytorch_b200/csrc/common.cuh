@@ -30,6 +30,12 @@ struct GemmLayer {
   int flat_w;    // offset of weight[n][k_h + enc_real] in the flat (torch-layout) vector
   int flat_b;    // offset of bias[n] in the flat vector
   int src;       // gemm index whose output is this layer's h-input (-1 for layer1)
+  // tcgen05 operand copy (mlp_tc.cu): k_tc = K the tensor-core path contracts over (the direction
+  // encoding of layers_dir[0] is hoisted out per ray, so k_tc = k_h there); per k-step of 8 the blob
+  // holds [hi slab0 | hi slab1 | lo slab0 | lo slab1], slab = [n][4 floats] (UMMA canonical K-major,
+  // no swizzle: 8-row core matrices 128 B apart, the two K halves one slab apart).
+  int k_tc;
+  int tc_off;
 };
 
 struct HeadLayer {
@@ -62,6 +68,7 @@ struct Plan {
 int build_plan(const nerfb200_arch_t* arch, Plan* plan);  // 0 or NERFB200_ERR_*
 void set_error(const char* fmt, ...);
 int check_cuda(cudaError_t e, const char* what);
+void count_launch();  // one call per kernel launched (nerfb200_launch_count)
 
 // launchers (one per .cu), all return NERFB200_OK or an error code
 int launch_pack(const Plan& p, const float* flat, float* blob, cudaStream_t s);

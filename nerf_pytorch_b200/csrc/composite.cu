@@ -215,6 +215,7 @@ int launch_composite_fwd(const float* raw, const float* z, const float* rays, in
   const int64_t blocks = (n_rays + kCompWarps - 1) / kCompWarps;
   composite_fwd_kernel<<<(unsigned)blocks, kCompWarps * 32, smem, s>>>(raw, z, rays, ray_stride, noise, n_rays,
                                                                        n_samples, noise_std, white_bkgd, out, weights);
+  count_launch();
   return check_cuda(cudaGetLastError(), "composite_fwd launch");
 }
 
@@ -225,6 +226,7 @@ int launch_composite_bwd(const float* raw, const float* z, const float* rays, in
   const int64_t blocks = (n_rays + kCompWarps - 1) / kCompWarps;
   composite_bwd_kernel<<<(unsigned)blocks, kCompWarps * 32, smem, s>>>(raw, z, rays, ray_stride, noise, g_out, n_rays,
                                                                        n_samples, noise_std, white_bkgd, d_raw);
+  count_launch();
   return check_cuda(cudaGetLastError(), "composite_bwd launch");
 }
 

@@ -268,6 +268,7 @@ int launch_mlp_fwd_simt(const Plan& p, const float* blob, const float* rays, int
                       "mlp_fwd smem attribute");
   if (rc) return rc;
   kern<<<(unsigned)tiles, kThreads, bytes, s>>>(p, sm, blob, rays, ray_stride, z, P, n_samples, raw, stash);
+  count_launch();
   return check_cuda(cudaGetLastError(), "mlp_fwd_simt launch");
 }
 
@@ -657,6 +658,7 @@ int launch_mlp_bwd_simt(const Plan& p, const float* blob, const float* rays, int
                         "mlp_bwd_dgrad smem attribute");
     if (rc) return rc;
     kern<<<(unsigned)tiles, kThreads, bytes, s>>>(p, sm, blob, d_raw, stash, gstash, P);
+    count_launch();
     rc = check_cuda(cudaGetLastError(), "mlp_bwd_dgrad launch");
     if (rc) return rc;
   }
@@ -674,6 +676,7 @@ int launch_mlp_bwd_simt(const Plan& p, const float* blob, const float* rays, int
     dim3 grid(split, items);
     mlp_bwd_wgrad_kernel<<<grid, kThreads, bytes, s>>>(p, rays, ray_stride, z, n_samples, d_raw, stash, gstash, P,
                                                        flat_grad);
+    count_launch();
     rc = check_cuda(cudaGetLastError(), "mlp_bwd_wgrad launch");
     if (rc) return rc;
   }

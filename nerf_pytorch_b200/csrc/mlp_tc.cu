@@ -1,13 +1,439 @@
-// mlp_tc.cu -- tcgen05 (5th-gen tensor core) implementation of the fused MLP forward.
-// Placeholder until the TMEM/UMMA pipeline lands: reports "unsupported" so that callers fail loudly.
+// mlp_tc.cu -- tcgen05 (5th-generation tensor core) implementation of the fused per-point forward
+//     points -> positional encoding -> FlexibleNeRFModel (nerf/train_utils.py:67, :8-25; nerf/models.py:233-256)
+// for hidden_size 128, fp32-faithful through a 3xTF32 split:
+//     x * w  ~=  x_hi*w_hi + x_lo*w_hi + x_hi*w_lo        (x_hi = tf32(x), x_lo = x - x_hi, same for w)
+// accumulated in fp32 in tensor memory (single-pass TF32/BF16 misses the
+// 1e-4 bar on the shipped checkpoints; the 3-term split meets it).
+//
+// Persistent kernel, one CTA per SM, 192 threads:
+//   warps 0-3  prologue/epilogue: thread r owns row r of the 128-point tile (= TMEM lane r).  Prologue:
+//              point generation + sin/cos encoding, split into hi/lo, written to shared memory in the UMMA
+//              canonical K-major layout.  Epilogue of every layer: tcgen05.ld the fp32 accumulator, + bias,
+//              ReLU, (stash), narrow heads (fc_alpha / fc_rgb / fc_out) as register dot products, split
+//              into hi/lo and tcgen05.st back into tensor memory as the NEXT layer's A operand.
+//   warp 4     MMA issuer: one elected lane issues tcgen05.mma.kind::tf32 (M=128, N=128|64, K=8 per
+//              instruction; three instructions per k-step), A from tensor memory (hidden activations) or
+//              shared memory (encodings), B = pre-split weights from the shared-memory ring.
+//   warp 5     weight producer: cp.async.bulk of one k-step of (hi, lo) weights per ring stage from the
+//              L2-resident blob, mbarrier complete_tx.
+// Tensor memory (512 columns): [0,128) accumulator, [128,256) A_hi, [256,384) A_lo.
+// The direction encoding enters layers_dir[0] through a per-ray bias computed on the CUDA cores in fp32
+// (it is constant along a ray: SURVEY.md section 7.3 item 5), so that layer contracts over K = 128 only.
 #include "common.cuh"
 
 namespace nerfb200 {
 
-int launch_mlp_fwd_tc(const Plan&, const float*, const float*, int, const float*, int64_t, int, float*, float*,
-                      cudaStream_t) {
-  set_error("mlp_fwd impl=1 (tcgen05) is not built into this library yet");
-  return NERFB200_ERR_UNSUPPORTED;
+namespace tc {
+
+constexpr int kEpiThreads = 128;
+constexpr int kThreadsTc = 192;
+constexpr int kStages = 12;          // weight ring depth
+constexpr int kStageBytes = 8192;    // one k-step of hi+lo weights for N = 128
+constexpr int kSlabBytes = 2048;     // 128 rows x 16 B
+constexpr int kMaxRaysPerTile = 10;
+constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kColAcc = 0, kColAhi = 128, kColAlo = 256;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// UMMA shared-memory descriptor, K-major, no swizzle: 8-row core matrices (8 x 16 B) `sbo` bytes apart
+// along M/N, the two K halves of one instruction `lbo` bytes apart.  Bit layout per the PTX ISA matrix
+// descriptor (cute::UMMA::SmemDescriptor): [0,14) addr>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version = 1.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) |
+         (1ull << 46);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, M = 128
+__device__ __forceinline__ uint32_t make_idesc(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+}
+__device__ __forceinline__ void mma_ss(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(d),
+      "l"(a), "l"(b), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a_tmem, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}\n" ::"r"(d),
+      "r"(a_tmem), "l"(b), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+#define NB_R32(v, o)                                                                                              \
+  "=r"(v[o + 0]), "=r"(v[o + 1]), "=r"(v[o + 2]), "=r"(v[o + 3]), "=r"(v[o + 4]), "=r"(v[o + 5]), "=r"(v[o + 6]), \
+      "=r"(v[o + 7])
+#define NB_W32(v, o)                                                                                       \
+  "r"(v[o + 0]), "r"(v[o + 1]), "r"(v[o + 2]), "r"(v[o + 3]), "r"(v[o + 4]), "r"(v[o + 5]), "r"(v[o + 6]), \
+      "r"(v[o + 7])
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,"
+      "%29,%30,%31}, [%32];\n"
+      : NB_R32(v, 0), NB_R32(v, 8), NB_R32(v, 16), NB_R32(v, 24)
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%32], "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,"
+      "%29,%30,%31};\n" ::NB_W32(v, 0),
+      NB_W32(v, 8), NB_W32(v, 16), NB_W32(v, 24), "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t tf32_hi(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+struct Smem {
+  // byte offsets from the 1024-aligned base
+  static constexpr int e_hi = 0;                         // 16 slabs (K <= 64) x 2 KB
+  static constexpr int e_lo = e_hi + 16 * kSlabBytes;
+  static constexpr int ring = e_lo + 16 * kSlabBytes;    // kStages x 8 KB
+  static constexpr int bias = ring + kStages * kStageBytes;   // kMaxGemm x 128 floats
+  static constexpr int headw = bias + kMaxGemm * 128 * 4;     // 4*128 + 3*64 floats (+pad) and 8 bias floats
+  static constexpr int viewb = headw + (4 * 128 + 3 * 64 + 16) * 4;  // kMaxRaysPerTile x 64
+  static constexpr int encd = viewb + kMaxRaysPerTile * 64 * 4;      // kMaxRaysPerTile x 32
+  static constexpr int bars = encd + kMaxRaysPerTile * 32 * 4;       // mbarriers
+  static constexpr int total = bars + 256;
+};
+
+}  // namespace tc
+
+using namespace tc;
+
+__global__ void __launch_bounds__(kThreadsTc, 1)
+mlp_fwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob, const float* __restrict__ rays,
+                  int ray_stride, const float* __restrict__ z, int64_t P, int S, int64_t n_tiles,
+                  float* __restrict__ raw, float* __restrict__ stash) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // 1 KB aligned base
+  float* s_bias = reinterpret_cast<float*>(sm + Smem::bias);
+  float* s_headw = reinterpret_cast<float*>(sm + Smem::headw);
+  float* s_viewb = reinterpret_cast<float*>(sm + Smem::viewb);
+  float* s_encd = reinterpret_cast<float*>(sm + Smem::encd);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + Smem::bars);
+  uint64_t* bar_full = bars;                 // [kStages]  weights landed
+  uint64_t* bar_empty = bars + kStages;      // [kStages]  stage consumed by the MMAs
+  uint64_t* bar_a = bars + 2 * kStages;      // A operand of the next layer is ready (128 arrivals)
+  uint64_t* bar_acc = bars + 2 * kStages + 1;  // accumulator of the current layer is complete
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 2);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&bar_full[i], 1);
+      mbar_init(&bar_empty[i], 1);
+    }
+    mbar_init(bar_a, kEpiThreads);
+    mbar_init(bar_acc, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)),
+                 "r"(kTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  // biases + head weights: once per CTA
+  for (int gi = 0; gi < p.n_gemm; ++gi)
+    for (int i = tid; i < p.g[gi].n; i += kThreadsTc) s_bias[gi * 128 + i] = blob[p.g[gi].b_off + i];
+  const int hw1 = p.h[0].n_out * p.h[0].k;
+  const int hw2 = p.n_head > 1 ? p.h[1].n_out * p.h[1].k : 0;
+  for (int i = tid; i < hw1; i += kThreadsTc) s_headw[i] = blob[p.h[0].w_off + i];
+  for (int i = tid; i < hw2; i += kThreadsTc) s_headw[hw1 + i] = blob[p.h[1].w_off + i];
+  float* s_headb = s_headw + ((hw1 + hw2 + 3) & ~3);
+  if (tid < 4) s_headb[tid] = blob[p.h[0].b_off + tid];
+  if (tid >= 4 && tid < 8) s_headb[tid] = p.n_head > 1 ? blob[p.h[1].b_off + tid - 4] : 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *s_tmem;
+
+  const int64_t my_tiles = (n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+  if (warp == 5) {
+    // ===================== weight producer =====================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int64_t it = 0; it < my_tiles; ++it) {
+        for (int gi = 0; gi < p.n_gemm; ++gi) {
+          const GemmLayer& g = p.g[gi];
+          const uint32_t bytes = 64u * g.n;
+          const uint8_t* src = reinterpret_cast<const uint8_t*>(blob + g.tc_off);
+          const int ksteps = g.k_tc >> 3;
+          for (int ks = 0; ks < ksteps; ++ks) {
+            mbar_wait(&bar_empty[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&bar_full[stage], bytes);
+            bulk_g2s(sm + Smem::ring + stage * kStageBytes, src + (size_t)ks * bytes, bytes, &bar_full[stage]);
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 4) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, a_phase = 0;
+      const uint32_t e_hi = smem_u32(sm + Smem::e_hi), e_lo = smem_u32(sm + Smem::e_lo);
+      for (int64_t it = 0; it < my_tiles; ++it) {
+        for (int gi = 0; gi < p.n_gemm; ++gi) {
+          const GemmLayer& g = p.g[gi];
+          const uint32_t idesc = make_idesc(g.n);
+          const uint32_t slab_b = 16u * g.n;  // bytes of one weight slab
+          const int ksteps = g.k_tc >> 3, ksteps_h = g.k_h >> 3;
+          mbar_wait(bar_a, a_phase);
+          a_phase ^= 1;
+          tc_fence_after();
+          for (int ks = 0; ks < ksteps; ++ks) {
+            mbar_wait(&bar_full[stage], phase);
+            tc_fence_after();
+            const uint32_t wb = smem_u32(sm + Smem::ring + stage * kStageBytes);
+            const uint64_t b_hi = make_desc(wb, slab_b, 128);
+            const uint64_t b_lo = make_desc(wb + 2 * slab_b, slab_b, 128);
+            const uint32_t acc0 = ks > 0 ? 1u : 0u;
+            if (ks < ksteps_h) {
+              const uint32_t a_hi = tmem + kColAhi + 8 * ks, a_lo = tmem + kColAlo + 8 * ks;
+              mma_ts(tmem + kColAcc, a_hi, b_hi, idesc, acc0);
+              mma_ts(tmem + kColAcc, a_lo, b_hi, idesc, 1u);
+              mma_ts(tmem + kColAcc, a_hi, b_lo, idesc, 1u);
+            } else {
+              const uint32_t off = (uint32_t)(ks - ksteps_h) * 2 * kSlabBytes;
+              const uint64_t a_hi = make_desc(e_hi + off, kSlabBytes, 128);
+              const uint64_t a_lo = make_desc(e_lo + off, kSlabBytes, 128);
+              mma_ss(tmem + kColAcc, a_hi, b_hi, idesc, acc0);
+              mma_ss(tmem + kColAcc, a_lo, b_hi, idesc, 1u);
+              mma_ss(tmem + kColAcc, a_hi, b_lo, idesc, 1u);
+            }
+            mma_commit(&bar_empty[stage]);  // frees the ring stage once these MMAs have read it
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
+          mma_commit(bar_acc);  // accumulator of layer gi complete
+        }
+      }
+    }
+  } else {
+    // ===================== prologue / epilogue warps (thread = row) =====================
+    const int row = tid;
+    const uint32_t lane_base = ((uint32_t)(warp * 32)) << 16;
+    uint32_t acc_phase = 0;
+    uint8_t* e_hi = sm + Smem::e_hi;
+    uint8_t* e_lo = sm + Smem::e_lo;
+    for (int64_t it = 0; it < my_tiles; ++it) {
+      const int64_t tile = blockIdx.x + it * gridDim.x;
+      const int64_t p0 = tile * kTileRows;
+      int64_t pt = p0 + row;
+      const bool valid = pt < P;
+      if (!valid) pt = P - 1;
+      const int64_t ray = pt / S;
+      const int64_t first_ray = p0 / S;
+      const int64_t last_pt = (p0 + kTileRows - 1 < P) ? p0 + kTileRows - 1 : P - 1;
+      const int n_rays_tile = (int)(last_pt / S - first_ray) + 1;
+      const int ray_slot = (int)(ray - first_ray);
+
+      // ---- prologue: encodings of this row -> E_hi / E_lo (canonical K-major slabs) ----
+      {
+        const float* rr = rays + ray * ray_stride;
+        const float zz = z[pt];
+        for (int c = 0; c < 3; ++c) {
+          const float x = __fadd_rn(rr[c], __fmul_rn(rr[3 + c], zz));  // pts = ro + rd * z (train_utils.py:67)
+          auto put = [&](int k, float v) {
+            const uint32_t hi = tf32_hi(v);
+            const float lo = v - __uint_as_float(hi);
+            const int off = (k >> 2) * kSlabBytes + row * 16 + (k & 3) * 4;
+            *reinterpret_cast<uint32_t*>(e_hi + off) = hi;
+            *reinterpret_cast<float*>(e_lo + off) = lo;
+          };
+          const int base = p.inc_xyz ? 3 : 0;
+          if (p.inc_xyz) put(c, x);
+          for (int f = 0; f < p.n_freq_xyz; ++f) {
+            float sn, cs;
+            sincosf(__fmul_rn(x, p.freq_xyz[f]), &sn, &cs);
+            put(base + 6 * f + c, sn);
+            put(base + 6 * f + 3 + c, cs);
+          }
+        }
+        for (int k = p.dim_xyz; k < p.dim_xyz_pad; ++k) {
+          const int off = (k >> 2) * kSlabBytes + row * 16 + (k & 3) * 4;
+          *reinterpret_cast<uint32_t*>(e_hi + off) = 0u;
+          *reinterpret_cast<uint32_t*>(e_lo + off) = 0u;
+        }
+      }
+      // ---- per-ray direction term of layers_dir[0]: vb[ray][n] = sum_k enc_dir(ray)[k] * W[n][H + k] ----
+      if (p.use_viewdirs) {
+        if (row < n_rays_tile * 3) {
+          const int j = row / 3, c = row - 3 * j;
+          const float v = rays[(first_ray + j) * ray_stride + 8 + c];
+          encode_coord(v, c, p.inc_dir, 0, p.n_freq_dir, p.freq_dir, s_encd + j * 32);
+        }
+        epi_bar();
+        const GemmLayer& gd = p.g[p.n_gemm - 1];
+        const float* wv = blob + gd.wt_off + (size_t)gd.k_h * gd.n;  // rows k_h.. of Wt[k][n]
+        for (int i = row; i < n_rays_tile * gd.n; i += kEpiThreads) {
+          const int j = i / gd.n, n = i - j * gd.n;
+          float a = 0.f;
+          for (int k = 0; k < p.dim_dir; ++k) a = fmaf(s_encd[j * 32 + k], wv[k * gd.n + n], a);
+          s_viewb[j * 64 + n] = a;
+        }
+      }
+      fence_proxy_async();  // E_hi / E_lo were written through the generic proxy; the MMAs read them via the async proxy
+      epi_bar();            // also publishes s_viewb
+      mbar_arrive(bar_a);
+
+      // ---- layers ----
+      float hacc[4];
+      for (int gi = 0; gi < p.n_gemm; ++gi) {
+        const GemmLayer& g = p.g[gi];
+        const bool has_next = gi + 1 < p.n_gemm;
+        int hsel = -1;
+        if (p.h[0].src == gi) hsel = 0;
+        if (p.n_head > 1 && p.h[1].src == gi) hsel = 1;
+        const float* hw = hsel == 1 ? s_headw + hw1 : s_headw;
+        const int hk = hsel >= 0 ? p.h[hsel].k : 0, hn = hsel >= 0 ? p.h[hsel].n_out : 0;
+        if (hsel >= 0) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) hacc[c] = s_headb[hsel * 4 + c];
+        }
+        const bool is_dir = p.use_viewdirs && gi == p.n_gemm - 1;
+        float* st = (stash && valid) ? stash + (size_t)P * g.cum_n + (size_t)pt * g.n : nullptr;
+
+        mbar_wait(bar_acc, acc_phase);
+        acc_phase ^= 1;
+        tc_fence_after();
+        for (int c0 = 0; c0 < g.n; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(tmem + lane_base + kColAcc + c0, v);
+          tmem_wait_ld();
+          uint32_t hi[32], lo[32];
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b = *reinterpret_cast<const float4*>(s_bias + gi * 128 + c0 + j);
+            float x[4] = {__uint_as_float(v[j]) + b.x, __uint_as_float(v[j + 1]) + b.y,
+                          __uint_as_float(v[j + 2]) + b.z, __uint_as_float(v[j + 3]) + b.w};
+            if (is_dir) {
+              const float4 vb = *reinterpret_cast<const float4*>(s_viewb + ray_slot * 64 + c0 + j);
+              x[0] += vb.x; x[1] += vb.y; x[2] += vb.z; x[3] += vb.w;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float y = g.relu ? fmaxf(x[q], 0.f) : x[q];
+              if (hsel >= 0) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                  if (c < hn) hacc[c] = fmaf(y, hw[c * hk + c0 + j + q], hacc[c]);
+              }
+              x[q] = y;
+              hi[j + q] = tf32_hi(y);
+              lo[j + q] = __float_as_uint(y - __uint_as_float(hi[j + q]));
+            }
+            if (st) *reinterpret_cast<float4*>(st + c0 + j) = make_float4(x[0], x[1], x[2], x[3]);
+          }
+          if (has_next) {
+            tmem_st32(tmem + lane_base + kColAhi + c0, hi);
+            tmem_st32(tmem + lane_base + kColAlo + c0, lo);
+          }
+        }
+        if (hsel >= 0 && valid) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            if (c < hn) raw[pt * 4 + p.h[hsel].out_col + c] = hacc[c];
+        }
+        if (has_next) {
+          tmem_wait_st();
+          tc_fence_before();
+          mbar_arrive(bar_a);
+        } else {
+          // the accumulator has been drained (wait::ld above); the next tile's first MMA is additionally
+          // ordered behind this thread by the bar_a arrival after the next prologue.
+          tc_fence_before();
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols));
+  }
+}
+
+int launch_mlp_fwd_tc(const Plan& p, const float* blob, const float* rays, int ray_stride, const float* z,
+                      int64_t n_rays, int n_samples, float* raw, float* stash, cudaStream_t s) {
+  if (p.hidden != 128) {
+    set_error("mlp_fwd impl=1 (tcgen05): hidden_size %d not supported (128 only); use impl=0", p.hidden);
+    return NERFB200_ERR_UNSUPPORTED;
+  }
+  if (p.dim_xyz_pad > 64 || p.dim_dir > 32) {
+    set_error("mlp_fwd impl=1 (tcgen05): encodings wider than 64 (xyz) / 32 (dir) not supported; use impl=0");
+    return NERFB200_ERR_UNSUPPORTED;
+  }
+  if ((kTileRows + n_samples - 1) / n_samples + 1 > kMaxRaysPerTile) {
+    set_error("mlp_fwd impl=1 (tcgen05): fewer than 16 samples per ray not supported; use impl=0");
+    return NERFB200_ERR_UNSUPPORTED;
+  }
+  const int64_t P = n_rays * n_samples;
+  const int64_t tiles = (P + kTileRows - 1) / kTileRows;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = (int)(tiles < sms ? tiles : sms);
+  const size_t bytes = Smem::total + 1024;
+  int rc = check_cuda(cudaFuncSetAttribute(mlp_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes),
+                      "mlp_fwd_tc smem attribute");
+  if (rc) return rc;
+  mlp_fwd_tc_kernel<<<grid, kThreadsTc, bytes, s>>>(p, blob, rays, ray_stride, z, P, n_samples, tiles, raw, stash);
+  count_launch();
+  return check_cuda(cudaGetLastError(), "mlp_fwd_tc launch");
 }
 
 }  // namespace nerfb200

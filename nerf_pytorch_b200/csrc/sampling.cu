@@ -49,6 +49,7 @@ int launch_sample_coarse(const float* rays, int ray_stride, int64_t n_rays, cons
   const int64_t blocks = (total + threads - 1) / threads;
   sample_coarse_kernel<<<(unsigned)blocks, threads, 0, s>>>(rays, ray_stride, n_rays, t_vals, t_rand, n_coarse,
                                                             perturb, lindisp, z);
+  count_launch();
   return check_cuda(cudaGetLastError(), "sample_coarse launch");
 }
 
@@ -71,6 +72,7 @@ int launch_encode(const Plan& p, int which, const float* x, int64_t n, float* ou
   const int threads = 256;
   const int64_t blocks = (n * 3 + threads - 1) / threads;
   encode_kernel<<<(unsigned)blocks, threads, 0, s>>>(p, which, x, n, out);
+  count_launch();
   return check_cuda(cudaGetLastError(), "encode launch");
 }
 
@@ -188,6 +190,7 @@ int launch_sample_pdf_merge(const float* z_coarse, const float* weights_coarse, 
   sample_pdf_merge_kernel<<<(unsigned)blocks, kPdfWarps * 32, smem, s>>>(
       z_coarse, weights_coarse, u, u_stride, cdf_in, n_rays, n_coarse, n_fine, npow2, z_fine, z_samples, inds,
       cdf_out);
+  count_launch();
   return check_cuda(cudaGetLastError(), "sample_pdf_merge launch");
 }
 
@@ -216,6 +219,22 @@ __global__ void pack_kernel(Plan p, const float* __restrict__ flat, float* __res
       } else if (idx >= g.b_off && idx < g.b_off + g.n) {
         val = flat[g.flat_b + (idx - g.b_off)];
         found = true;
+      } else if (idx >= g.tc_off && idx < g.tc_off + 2 * g.k_tc * g.n) {
+        // [kstep][hi|lo][slab 0|1][n][4]: element (n, k = kstep*8 + slab*4 + j)
+        const int e = idx - g.tc_off;
+        const int per_step = 16 * g.n;
+        const int ks = e / per_step, r = e - ks * per_step;
+        const int part = r / (8 * g.n), r2 = r - part * 8 * g.n;
+        const int slab = r2 / (4 * g.n), r3 = r2 - slab * 4 * g.n;
+        const int nn = r3 >> 2, j = r3 & 3;
+        const int k = ks * 8 + slab * 4 + j;
+        float w = 0.f;
+        if (k < g.k_h || k - g.k_h < g.enc_real) w = flat[g.flat_w + nn * in_real + k];
+        uint32_t hb;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(w));
+        const float hi = __uint_as_float(hb);
+        val = part == 0 ? hi : w - hi;
+        found = true;
       }
     }
     for (int hi = 0; hi < p.n_head && !found; ++hi) {
@@ -239,6 +258,7 @@ int launch_pack(const Plan& p, const float* flat, float* blob, cudaStream_t s) {
   int blocks = (p.blob_floats + threads - 1) / threads;
   if (blocks > 1184) blocks = 1184;
   pack_kernel<<<blocks, threads, 0, s>>>(p, flat, blob);
+  count_launch();
   return check_cuda(cudaGetLastError(), "pack launch");
 }
 
@@ -268,6 +288,7 @@ int launch_adam(float* p, const float* g, float* m, float* v, int64_t n, int ste
   if (blocks > 148 * 8) blocks = 148 * 8;
   adam_kernel<<<(unsigned)blocks, threads, 0, s>>>(p, g, m, v, n, (float)(lr / bc1), (float)(1.0 / sqrt(bc2)), b1, b2,
                                                    eps, grad_scale);
+  count_launch();
   return check_cuda(cudaGetLastError(), "adam launch");
 }
 

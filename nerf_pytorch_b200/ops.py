@@ -34,6 +34,11 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def launch_count() -> int:
+    """Kernels launched by libnerfb200.so in this process so far."""
+    return int(_lib.load().nerfb200_launch_count())
+
+
 def frequency_bands(n: int, log_sampling: bool) -> torch.Tensor:
     """The bands exactly as the reference builds them (nerf/nerf_helpers.py:131-147), fp32, on CPU."""
     if n == 0:

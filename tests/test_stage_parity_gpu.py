@@ -125,7 +125,8 @@ def test_sample_pdf_indices_exact_given_cdf_and_values(name):
     assert (cdf2.cpu() - aux["cdf"]).abs().max() < 1e-6
     same = inds2.cpu().long() == aux["inds"]
     assert (~same).sum().item() <= max(2, inds2.numel() // 2000), (~same).sum().item()
-    assert ((zs2.cpu() - aux["z_samples"]).abs()[same]).max() < 2e-5
+    # (u - cdf_below) / denom amplifies a 1-ulp cdf difference by up to 1/1e-5 inside a bin
+    assert ((zs2.cpu() - aux["z_samples"]).abs()[same]).max() < 5e-4
     bin_w = (aux["z_coarse"][:, 1:] - aux["z_coarse"][:, :-1]).max().item()
     assert (zs2.cpu() - aux["z_samples"]).abs().max() <= 1.01 * bin_w
     assert (z_fine2[:, 1:] >= z_fine2[:, :-1]).all()

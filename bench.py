@@ -200,6 +200,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     impl = {"simt": ops.IMPL_SIMT, "tc": ops.IMPL_TC}[args.kernels]
+    if args.arch == "A2":
+        impl, args.kernels = ops.IMPL_SIMT, "simt"   # hidden 256: fp32 CUDA-core kernels only
     nb.set_default_impl(impl)
     parallel.enable_gradient_sync()
 
@@ -305,7 +307,7 @@ def run_ours(args):
                     "algorithmic_flops": flops_fwd}
             raw, stash = ops.mlp_fwd(arch, blob, rays, z, impl=impl, want_stash=True)
             G = torch.randn_like(raw)
-            tb = t_alone(lambda: ops.mlp_bwd(arch, blob, rays, z, G, stash))
+            tb = t_alone(lambda: ops.mlp_bwd(arch, blob, rays, z, G, stash, impl=impl))
             achb = 2 * flops_fwd / (tb * 1e-3) / 1e12
             roof_bwd = {"kernel": "mlp_bwd (dgrad + wgrad kernels, fine pass)", "bound": "tensor", "achieved": achb,
                         "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achb / peaks["bf16_tflops"], "ms": tb}
@@ -345,7 +347,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--arch", default="A1", choices=list(ARCHS))
-    ap.add_argument("--kernels", default=os.environ.get("NERFB200_KERNELS", "simt"), choices=["simt", "tc"])
+    ap.add_argument("--kernels", default=os.environ.get("NERFB200_KERNELS", "tc"), choices=["simt", "tc"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

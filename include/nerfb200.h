@@ -65,6 +65,9 @@ int32_t nerfb200_version(void);
 const char* nerfb200_last_error(void);
 /* number of CUDA kernels this library has launched in this process (all threads) */
 int64_t nerfb200_launch_count(void);
+/* debug hook: device buffer of 4 int64 per CTA receiving the tcgen05 kernel's cycle counters
+ * [prologue, wait-for-MMA, epilogue, total] of its epilogue thread 0; NULL switches it off. */
+void nerfb200_debug_tc_profile(void* buf);
 
 /* ---- parameters -------------------------------------------------------------------------------
  * Canonical order of the linears ("slots"): layer1, layers_xyz[0..num_layers-2], then

@@ -136,6 +136,10 @@ int build_plan(const nerfb200_arch_t* a, Plan* p) {
     p->n_head = 1;
   }
   p->n_gemm = ng;
+  p->enc_cum[0] = cum;
+  cum += p->dim_xyz_pad;
+  p->enc_cum[1] = cum;
+  cum += p->dim_dir_pad;
   p->sum_n = cum;
   p->blob_floats = blob;
   p->flat_floats = flat;
@@ -234,6 +238,7 @@ extern "C" {
 int32_t nerfb200_version(void) { return NERFB200_VERSION; }
 const char* nerfb200_last_error(void) { return g_err; }
 int64_t nerfb200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+void nerfb200_debug_tc_profile(void* buf) { set_tc_profile(buf); }
 
 int64_t nerfb200_num_linear(const nerfb200_arch_t* arch) {
   Plan p;
@@ -356,9 +361,8 @@ int32_t nerfb200_mlp_bwd(const nerfb200_arch_t* arch, const float* blob, const f
     set_error("mlp_bwd: null pointer");
     return NERFB200_ERR_INVALID;
   }
-  (void)impl;  // the backward currently has one implementation (fp32 CUDA cores)
-  return launch_mlp_bwd_simt(p, blob, rays, ray_stride, z, n_rays, n_samples, d_raw, stash, gstash, flat_grad,
-                             static_cast<cudaStream_t>(stream));
+  return launch_mlp_bwd(p, blob, rays, ray_stride, z, n_rays, n_samples, d_raw, stash, gstash, flat_grad, impl,
+                        static_cast<cudaStream_t>(stream));
 }
 
 int32_t nerfb200_composite_fwd(const float* raw, const float* z, const float* rays, int32_t ray_stride,
@@ -507,7 +511,6 @@ int32_t nerfb200_render_bwd(const nerfb200_arch_t* arch_c, const nerfb200_arch_t
     set_error("render_bwd: null pointer or empty batch");
     return NERFB200_ERR_INVALID;
   }
-  (void)impl;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   Workspace w;
   carve(pc, fine ? &pf : nullptr, *opts, n_rays, /*training=*/1, &w);
@@ -518,15 +521,15 @@ int32_t nerfb200_render_bwd(const nerfb200_arch_t* arch_c, const nerfb200_arch_t
   if (fine) {
     NB_TRY(launch_composite_bwd(F(w.raw_f), F(w.z_f), rays, ray_stride, opts->noise_std > 0.f ? noise_f : nullptr,
                                 g_fine, n_rays, ns, opts->noise_std, opts->white_bkgd, F(w.d_raw), s));
-    NB_TRY(launch_mlp_bwd_simt(pf, blob_f, rays, ray_stride, F(w.z_f), n_rays, ns, F(w.d_raw), F(w.stash_f),
-                               F(w.gstash), flat_grad_f, s));
+    NB_TRY(launch_mlp_bwd(pf, blob_f, rays, ray_stride, F(w.z_f), n_rays, ns, F(w.d_raw), F(w.stash_f), F(w.gstash),
+                          flat_grad_f, impl, s));
   }
   // the coarse weights feed the resampler only through a detach (train_utils.py:103), so the
   // coarse net's gradient comes from rgb/disp/acc_coarse alone.
   NB_TRY(launch_composite_bwd(F(w.raw_c), F(w.z_c), rays, ray_stride, opts->noise_std > 0.f ? noise_c : nullptr,
                               g_coarse, n_rays, nc, opts->noise_std, opts->white_bkgd, F(w.d_raw), s));
-  NB_TRY(launch_mlp_bwd_simt(pc, blob_c, rays, ray_stride, F(w.z_c), n_rays, nc, F(w.d_raw), F(w.stash_c),
-                             F(w.gstash), flat_grad_c, s));
+  NB_TRY(launch_mlp_bwd(pc, blob_c, rays, ray_stride, F(w.z_c), n_rays, nc, F(w.d_raw), F(w.stash_c), F(w.gstash),
+                        flat_grad_c, impl, s));
   return NERFB200_OK;
 }
 

@@ -53,7 +53,8 @@ struct Plan {
   int n_trunk;  // gemm layers 0..n_trunk-1 are layer1 + layers_xyz
   int n_head;
   int hidden;
-  int sum_n;  // sum of n over all gemm layers = floats stashed per point
+  int sum_n;  // floats stashed per point: every gemm layer's output + the two padded encodings
+  int enc_cum[2];  // stash slice of the xyz / direction encoding: base + n_points * enc_cum[sel], width dim_*_pad
   int dim_xyz, dim_xyz_pad, dim_dir, dim_dir_pad;
   int n_freq_xyz, n_freq_dir, inc_xyz, inc_dir;
   int blob_floats, flat_floats;
@@ -77,9 +78,11 @@ int launch_sample_coarse(const float* rays, int ray_stride, int64_t n_rays, cons
 int launch_encode(const Plan& p, int which, const float* x, int64_t n, float* out, cudaStream_t s);
 int launch_mlp_fwd_simt(const Plan& p, const float* blob, const float* rays, int ray_stride, const float* z,
                         int64_t n_rays, int n_samples, float* raw, float* stash, cudaStream_t s);
-int launch_mlp_bwd_simt(const Plan& p, const float* blob, const float* rays, int ray_stride, const float* z,
-                        int64_t n_rays, int n_samples, const float* d_raw, const float* stash, float* gstash,
-                        float* flat_grad, cudaStream_t s);
+int launch_mlp_bwd(const Plan& p, const float* blob, const float* rays, int ray_stride, const float* z,
+                   int64_t n_rays, int n_samples, const float* d_raw, const float* stash, float* gstash,
+                   float* flat_grad, int impl, cudaStream_t s);
+int launch_wgrad_tc(const Plan& p, const float* rays, int ray_stride, const float* z, int64_t n_rays, int n_samples,
+                    const float* stash, const float* gstash, float* flat_grad, cudaStream_t s);
 int launch_composite_fwd(const float* raw, const float* z, const float* rays, int ray_stride, const float* noise,
                          int64_t n_rays, int n_samples, float noise_std, int white_bkgd, float* out,
                          float* weights, cudaStream_t s);
@@ -92,6 +95,7 @@ int launch_sample_pdf_merge(const float* z_coarse, const float* weights_coarse, 
 int launch_adam(float* p, const float* g, float* m, float* v, int64_t n, int step, float lr, float b1, float b2,
                 float eps, float grad_scale, cudaStream_t s);
 // tcgen05 path (mlp_tc.cu)
+void set_tc_profile(void* p);
 int launch_mlp_fwd_tc(const Plan& p, const float* blob, const float* rays, int ray_stride, const float* z,
                       int64_t n_rays, int n_samples, float* raw, float* stash, cudaStream_t s);
 

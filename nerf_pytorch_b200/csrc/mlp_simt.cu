@@ -17,6 +17,7 @@
 #include <type_traits>
 
 #include "common.cuh"
+#include "wgrad_items.cuh"
 
 namespace nerfb200 {
 
@@ -209,7 +210,28 @@ mlp_fwd_simt_kernel(const __grid_constant__ Plan p, const FwdSmem sm, const floa
   if (tid >= 4 && tid < 8 && p.n_head > 1) hb[tid] = blob[p.h[1].b_off + tid - 4];
 
   encode_tile(p, rays, ray_stride, z, p0, P, S, kTileRows, encx, sm.encx_ld, encd, sm.encd_ld, tid, kThreads);
-  // (the first __syncthreads inside gemm_tile orders these writes before any read)
+  if (stash) {  // the backward reads the encodings back instead of recomputing 60 sin/cos per point
+    __syncthreads();
+    float* sx = stash + (size_t)P * p.enc_cum[0];
+    const int vx = p.dim_xyz_pad / 4;
+    for (int i = tid; i < kTileRows * vx; i += kThreads) {
+      const int row = i / vx, cc = i - row * vx;
+      if (p0 + row < P)
+        *reinterpret_cast<float4*>(sx + (size_t)(p0 + row) * p.dim_xyz_pad + 4 * cc) =
+            *reinterpret_cast<const float4*>(encx + row * sm.encx_ld + 4 * cc);
+    }
+    if (encd) {
+      float* sd = stash + (size_t)P * p.enc_cum[1];
+      const int vd = p.dim_dir_pad / 4;
+      for (int i = tid; i < kTileRows * vd; i += kThreads) {
+        const int row = i / vd, cc = i - row * vd;
+        if (p0 + row < P)
+          *reinterpret_cast<float4*>(sd + (size_t)(p0 + row) * p.dim_dir_pad + 4 * cc) =
+              *reinterpret_cast<const float4*>(encd + row * sm.encd_ld + 4 * cc);
+      }
+    }
+  }
+  // (the first __syncthreads inside gemm_tile orders the encoding writes before any read)
 
   const int ty = tid >> 4, tx = tid & 15;
   for (int gi = 0; gi < p.n_gemm; ++gi) {
@@ -395,57 +417,6 @@ mlp_bwd_dgrad_kernel(const __grid_constant__ Plan p, const BwdSmem sm, const flo
 // =============================================================================================
 constexpr int kWgPts = 32;  // points per pipeline stage
 
-struct WgItem {
-  int kind;      // 0: gemm weight block with X from the stash, 1: X = encoding, 2: head
-  int t;         // gemm index (kind 0/1) or head index (kind 2)
-  int n0, nblk;  // output-row block
-  int k0, kblk;  // input-column block (kind 0: offset in the h part; kind 1: padded-to-16 encoding width)
-  int bias;      // this item also reduces the bias gradient
-};
-
-__host__ __device__ inline int wg_item_count(const Plan& p) {
-  int n = 0;
-  for (int t = 0; t < p.n_gemm; ++t) {
-    const int nb = p.g[t].n / 128 > 0 ? (p.g[t].n + 127) / 128 : 1;
-    const int kb = (p.g[t].k_h + 127) / 128;
-    n += nb * (kb + (p.g[t].k_enc > 0 ? 1 : 0));
-  }
-  return n + p.n_head;
-}
-
-__device__ inline WgItem wg_decode(const Plan& p, int item) {
-  WgItem it;
-  for (int t = 0; t < p.n_gemm; ++t) {
-    const GemmLayer& g = p.g[t];
-    const int nb = (g.n + 127) / 128;
-    const int kb = (g.k_h + 127) / 128;
-    const int per = kb + (g.k_enc > 0 ? 1 : 0);
-    if (item < nb * per) {
-      const int bn = item / per, bk = item - bn * per;
-      it.t = t;
-      it.n0 = bn * 128;
-      it.nblk = min(128, g.n - it.n0);
-      if (bk < kb) {
-        it.kind = 0;
-        it.k0 = bk * 128;
-        it.kblk = min(128, g.k_h - it.k0);
-        it.bias = (bk == 0);
-      } else {
-        it.kind = 1;
-        it.k0 = 0;
-        it.kblk = (g.enc_real + 15) & ~15;
-        it.bias = (kb == 0);
-      }
-      return it;
-    }
-    item -= nb * per;
-  }
-  it.kind = 2;
-  it.t = item;
-  it.n0 = 0; it.nblk = p.h[item].n_out; it.k0 = 0; it.kblk = p.h[item].k; it.bias = 1;
-  return it;
-}
-
 // register-tile accumulation for one item: RN rows (n = ty*RN + r) x RK cols (k = tx + 16*i)
 template <int RN, int RK>
 __device__ __forceinline__ void wgrad_block(const Plan& p, const WgItem& it, const float* __restrict__ rays,
@@ -489,32 +460,15 @@ __device__ __forceinline__ void wgrad_block(const Plan& p, const WgItem& it, con
         else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
       }
     } else {
-      // recompute the encoding of these points (cheaper than stashing 63 floats per point)
-      const int rows = (int)min((int64_t)kWgPts, pt_end - q0);
-      float* e = xs[buf];
-      const int real = g.enc_real;
-      if (g.enc_sel == 0) {
-        for (int i = tid; i < rows * 3; i += kThreads) {
-          const int row = i / 3, c = i - row * 3;
-          const int64_t pt = q0 + row, ray = pt / S;
-          const float x = __fadd_rn(rays[ray * ray_stride + c], __fmul_rn(rays[ray * ray_stride + 3 + c], z[pt]));
-          encode_coord(x, c, p.inc_xyz, 0, p.n_freq_xyz, p.freq_xyz, e + row * ldx);
-        }
-      } else {
-        for (int i = tid; i < rows * 3; i += kThreads) {
-          const int row = i / 3, c = i - row * 3;
-          const int64_t ray = (q0 + row) / S;
-          encode_coord(rays[ray * ray_stride + 8 + c], c, p.inc_dir, 0, p.n_freq_dir, p.freq_dir, e + row * ldx);
-        }
-      }
-      const int padc = it.kblk - real;
-      for (int i = tid; i < rows * padc; i += kThreads) {
-        const int row = i / padc, c = i - row * padc;
-        e[row * ldx + real + c] = 0.f;
-      }
-      for (int i = tid; i < (kWgPts - rows) * it.kblk; i += kThreads) {
-        const int row = rows + i / it.kblk, c = i % it.kblk;
-        e[row * ldx + c] = 0.f;
+      // encoded-input columns: read the stashed encoding (zero in its padding columns)
+      const int ew = g.enc_sel ? p.dim_dir_pad : p.dim_xyz_pad;
+      const float* E = stash + (size_t)P * p.enc_cum[g.enc_sel];
+      const int vx = it.kblk / 4;
+      for (int i = tid; i < kWgPts * vx; i += kThreads) {
+        const int pp = i / vx, cc = i - pp * vx;
+        float* dst = xs[buf] + pp * ldx + cc * 4;
+        if (q0 + pp < pt_end && 4 * cc < ew) cp_async16(dst, E + (size_t)(q0 + pp) * ew + cc * 4);
+        else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
     cp_async_commit();
@@ -605,9 +559,9 @@ __global__ void __launch_bounds__(kThreads, 2)
 mlp_bwd_wgrad_kernel(const __grid_constant__ Plan p, const float* __restrict__ rays, int ray_stride,
                      const float* __restrict__ z, int S, const float* __restrict__ d_raw,
                      const float* __restrict__ stash, const float* __restrict__ gstash, int64_t P,
-                     float* __restrict__ flat_grad) {
+                     float* __restrict__ flat_grad, int item_base) {
   extern __shared__ __align__(16) float smem[];
-  const WgItem it = wg_decode(p, blockIdx.y);
+  const WgItem it = wg_decode(p, blockIdx.y + item_base);
   // contiguous point range of this CTA, in units of kWgPts
   const int64_t stages = (P + kWgPts - 1) / kWgPts;
   const int64_t per = (stages + gridDim.x - 1) / gridDim.x;
@@ -645,42 +599,57 @@ mlp_bwd_wgrad_kernel(const __grid_constant__ Plan p, const float* __restrict__ r
 #undef NB_WG
 }
 
-int launch_mlp_bwd_simt(const Plan& p, const float* blob, const float* rays, int ray_stride, const float* z,
-                        int64_t n_rays, int n_samples, const float* d_raw, const float* stash, float* gstash,
-                        float* flat_grad, cudaStream_t s) {
+int launch_dgrad_simt(const Plan& p, const float* blob, const float* d_raw, const float* stash, float* gstash,
+                      int64_t P, cudaStream_t s) {
+  const BwdSmem sm = bwd_smem_layout(p);
+  const size_t bytes = (size_t)sm.total_floats * sizeof(float);
+  const int64_t tiles = (P + kTileRows - 1) / kTileRows;
+  auto kern = p.hidden == 256 ? mlp_bwd_dgrad_kernel<4> : mlp_bwd_dgrad_kernel<2>;
+  int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes),
+                      "mlp_bwd_dgrad smem attribute");
+  if (rc) return rc;
+  kern<<<(unsigned)tiles, kThreads, bytes, s>>>(p, sm, blob, d_raw, stash, gstash, P);
+  count_launch();
+  return check_cuda(cudaGetLastError(), "mlp_bwd_dgrad launch");
+}
+
+// weight-gradient items [item_base, item_base + n_items) of wgrad_items.cuh on the CUDA cores
+int launch_wgrad_simt(const Plan& p, const float* rays, int ray_stride, const float* z, int n_samples,
+                      const float* d_raw, const float* stash, const float* gstash, int64_t P, float* flat_grad,
+                      int item_base, int n_items, cudaStream_t s) {
+  if (n_items <= 0) return NERFB200_OK;
+  const size_t bytes = (size_t)2 * kWgPts * (132 + 132) * sizeof(float);
+  int rc = check_cuda(
+      cudaFuncSetAttribute(mlp_bwd_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes),
+      "mlp_bwd_wgrad smem attribute");
+  if (rc) return rc;
+  const int64_t stages = (P + kWgPts - 1) / kWgPts;
+  int split = (int)((148 * 2 * 4 + n_items - 1) / n_items);
+  if (split > 1184) split = 1184;
+  if (split > stages) split = (int)stages;
+  if (split < 1) split = 1;
+  dim3 grid(split, n_items);
+  mlp_bwd_wgrad_kernel<<<grid, kThreads, bytes, s>>>(p, rays, ray_stride, z, n_samples, d_raw, stash, gstash, P,
+                                                     flat_grad, item_base);
+  count_launch();
+  return check_cuda(cudaGetLastError(), "mlp_bwd_wgrad launch");
+}
+
+int launch_mlp_bwd(const Plan& p, const float* blob, const float* rays, int ray_stride, const float* z,
+                   int64_t n_rays, int n_samples, const float* d_raw, const float* stash, float* gstash,
+                   float* flat_grad, int impl, cudaStream_t s) {
   const int64_t P = n_rays * n_samples;
-  {
-    const BwdSmem sm = bwd_smem_layout(p);
-    const size_t bytes = (size_t)sm.total_floats * sizeof(float);
-    const int64_t tiles = (P + kTileRows - 1) / kTileRows;
-    auto kern = p.hidden == 256 ? mlp_bwd_dgrad_kernel<4> : mlp_bwd_dgrad_kernel<2>;
-    int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes),
-                        "mlp_bwd_dgrad smem attribute");
+  int rc = launch_dgrad_simt(p, blob, d_raw, stash, gstash, P, s);
+  if (rc) return rc;
+  const int items = wg_item_count(p);
+  if (impl == 1 && p.hidden == 128) {
+    // tensor cores for every GEMM-shaped item, CUDA cores for the 1..4-row heads
+    rc = launch_wgrad_tc(p, rays, ray_stride, z, n_rays, n_samples, stash, gstash, flat_grad, s);
     if (rc) return rc;
-    kern<<<(unsigned)tiles, kThreads, bytes, s>>>(p, sm, blob, d_raw, stash, gstash, P);
-    count_launch();
-    rc = check_cuda(cudaGetLastError(), "mlp_bwd_dgrad launch");
-    if (rc) return rc;
+    return launch_wgrad_simt(p, rays, ray_stride, z, n_samples, d_raw, stash, gstash, P, flat_grad,
+                             items - p.n_head, p.n_head, s);
   }
-  {
-    const int items = wg_item_count(p);
-    const size_t bytes = (size_t)2 * kWgPts * (132 + 132) * sizeof(float);
-    int rc = check_cuda(
-        cudaFuncSetAttribute(mlp_bwd_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes),
-        "mlp_bwd_wgrad smem attribute");
-    if (rc) return rc;
-    const int64_t stages = (P + kWgPts - 1) / kWgPts;
-    int split = (int)((148 * 2 * 4 + items - 1) / items);
-    if (split > stages) split = (int)stages;
-    if (split < 1) split = 1;
-    dim3 grid(split, items);
-    mlp_bwd_wgrad_kernel<<<grid, kThreads, bytes, s>>>(p, rays, ray_stride, z, n_samples, d_raw, stash, gstash, P,
-                                                       flat_grad);
-    count_launch();
-    rc = check_cuda(cudaGetLastError(), "mlp_bwd_wgrad launch");
-    if (rc) return rc;
-  }
-  return NERFB200_OK;
+  return launch_wgrad_simt(p, rays, ray_stride, z, n_samples, d_raw, stash, gstash, P, flat_grad, 0, items, s);
 }
 
 }  // namespace nerfb200

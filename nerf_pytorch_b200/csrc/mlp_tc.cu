@@ -20,8 +20,12 @@
 // The direction encoding enters layers_dir[0] through a per-ray bias computed on the CUDA cores in fp32
 // (it is constant along a ray: SURVEY.md section 7.3 item 5), so that layer contracts over K = 128 only.
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace nerfb200 {
+
+static long long* g_tc_prof = nullptr;  // debug hook: per-CTA cycle counters (nerfb200_debug_tc_profile)
+void set_tc_profile(void* p) { g_tc_prof = static_cast<long long*>(p); }
 
 namespace tc {
 
@@ -33,106 +37,6 @@ constexpr int kSlabBytes = 2048;     // 128 rows x 16 B
 constexpr int kMaxRaysPerTile = 10;
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kColAcc = 0, kColAhi = 128, kColAlo = 256;
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra WAIT_DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "WAIT_DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-
-// UMMA shared-memory descriptor, K-major, no swizzle: 8-row core matrices (8 x 16 B) `sbo` bytes apart
-// along M/N, the two K halves of one instruction `lbo` bytes apart.  Bit layout per the PTX ISA matrix
-// descriptor (cute::UMMA::SmemDescriptor): [0,14) addr>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version = 1.
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) |
-         (1ull << 46);
-}
-// instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, M = 128
-__device__ __forceinline__ uint32_t make_idesc(int n) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
-}
-__device__ __forceinline__ void mma_ss(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(d),
-      "l"(a), "l"(b), "r"(idesc), "r"(acc)
-      : "memory");
-}
-__device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a_tmem, uint64_t b, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}\n" ::"r"(d),
-      "r"(a_tmem), "l"(b), "r"(idesc), "r"(acc)
-      : "memory");
-}
-__device__ __forceinline__ void mma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-
-#define NB_R32(v, o)                                                                                              \
-  "=r"(v[o + 0]), "=r"(v[o + 1]), "=r"(v[o + 2]), "=r"(v[o + 3]), "=r"(v[o + 4]), "=r"(v[o + 5]), "=r"(v[o + 6]), \
-      "=r"(v[o + 7])
-#define NB_W32(v, o)                                                                                       \
-  "r"(v[o + 0]), "r"(v[o + 1]), "r"(v[o + 2]), "r"(v[o + 3]), "r"(v[o + 4]), "r"(v[o + 5]), "r"(v[o + 6]), \
-      "r"(v[o + 7])
-
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,"
-      "%29,%30,%31}, [%32];\n"
-      : NB_R32(v, 0), NB_R32(v, 8), NB_R32(v, 16), NB_R32(v, 24)
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%32], "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,"
-      "%29,%30,%31};\n" ::NB_W32(v, 0),
-      NB_W32(v, 8), NB_W32(v, 16), NB_W32(v, 24), "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
-__device__ __forceinline__ uint32_t tf32_hi(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return r;
-}
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 struct Smem {
   // byte offsets from the 1024-aligned base
@@ -154,7 +58,7 @@ using namespace tc;
 __global__ void __launch_bounds__(kThreadsTc, 1)
 mlp_fwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob, const float* __restrict__ rays,
                   int ray_stride, const float* __restrict__ z, int64_t P, int S, int64_t n_tiles,
-                  float* __restrict__ raw, float* __restrict__ stash) {
+                  float* __restrict__ raw, float* __restrict__ stash, long long* __restrict__ prof) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // 1 KB aligned base
   float* s_bias = reinterpret_cast<float*>(sm + Smem::bias);
@@ -268,7 +172,9 @@ mlp_fwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
     uint32_t acc_phase = 0;
     uint8_t* e_hi = sm + Smem::e_hi;
     uint8_t* e_lo = sm + Smem::e_lo;
+    long long t_pro = 0, t_wait = 0, t_epi = 0, t_all = clock64();
     for (int64_t it = 0; it < my_tiles; ++it) {
+      long long t0 = clock64();
       const int64_t tile = blockIdx.x + it * gridDim.x;
       const int64_t p0 = tile * kTileRows;
       int64_t pt = p0 + row;
@@ -284,9 +190,11 @@ mlp_fwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
       {
         const float* rr = rays + ray * ray_stride;
         const float zz = z[pt];
+        float* sx = (stash && valid) ? stash + (size_t)P * p.enc_cum[0] + (size_t)pt * p.dim_xyz_pad : nullptr;
         for (int c = 0; c < 3; ++c) {
           const float x = __fadd_rn(rr[c], __fmul_rn(rr[3 + c], zz));  // pts = ro + rd * z (train_utils.py:67)
           auto put = [&](int k, float v) {
+            if (sx) sx[k] = v;
             const uint32_t hi = tf32_hi(v);
             const float lo = v - __uint_as_float(hi);
             const int off = (k >> 2) * kSlabBytes + row * 16 + (k & 3) * 4;
@@ -303,6 +211,7 @@ mlp_fwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
           }
         }
         for (int k = p.dim_xyz; k < p.dim_xyz_pad; ++k) {
+          if (sx) sx[k] = 0.f;
           const int off = (k >> 2) * kSlabBytes + row * 16 + (k & 3) * 4;
           *reinterpret_cast<uint32_t*>(e_hi + off) = 0u;
           *reinterpret_cast<uint32_t*>(e_lo + off) = 0u;
@@ -327,7 +236,12 @@ mlp_fwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
       }
       fence_proxy_async();  // E_hi / E_lo were written through the generic proxy; the MMAs read them via the async proxy
       epi_bar();            // also publishes s_viewb
+      if (stash && valid && p.use_viewdirs) {
+        float* sd = stash + (size_t)P * p.enc_cum[1] + (size_t)pt * p.dim_dir_pad;
+        for (int k = 0; k < p.dim_dir_pad; ++k) sd[k] = k < p.dim_dir ? s_encd[ray_slot * 32 + k] : 0.f;
+      }
       mbar_arrive(bar_a);
+      t_pro += clock64() - t0;
 
       // ---- layers ----
       float hacc[4];
@@ -346,9 +260,12 @@ mlp_fwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
         const bool is_dir = p.use_viewdirs && gi == p.n_gemm - 1;
         float* st = (stash && valid) ? stash + (size_t)P * g.cum_n + (size_t)pt * g.n : nullptr;
 
+        t0 = clock64();
         mbar_wait(bar_acc, acc_phase);
         acc_phase ^= 1;
         tc_fence_after();
+        const long long t1 = clock64();
+        t_wait += t1 - t0;
         for (int c0 = 0; c0 < g.n; c0 += 32) {
           uint32_t v[32];
           tmem_ld32(tmem + lane_base + kColAcc + c0, v);
@@ -396,7 +313,14 @@ mlp_fwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
           // ordered behind this thread by the bar_a arrival after the next prologue.
           tc_fence_before();
         }
+        t_epi += clock64() - t1;
       }
+    }
+    if (prof && tid == 0) {
+      prof[blockIdx.x * 4 + 0] = t_pro;
+      prof[blockIdx.x * 4 + 1] = t_wait;
+      prof[blockIdx.x * 4 + 2] = t_epi;
+      prof[blockIdx.x * 4 + 3] = clock64() - t_all;
     }
   }
 
@@ -431,7 +355,7 @@ int launch_mlp_fwd_tc(const Plan& p, const float* blob, const float* rays, int r
   int rc = check_cuda(cudaFuncSetAttribute(mlp_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes),
                       "mlp_fwd_tc smem attribute");
   if (rc) return rc;
-  mlp_fwd_tc_kernel<<<grid, kThreadsTc, bytes, s>>>(p, blob, rays, ray_stride, z, P, n_samples, tiles, raw, stash);
+  mlp_fwd_tc_kernel<<<grid, kThreadsTc, bytes, s>>>(p, blob, rays, ray_stride, z, P, n_samples, tiles, raw, stash, g_tc_prof);
   count_launch();
   return check_cuda(cudaGetLastError(), "mlp_fwd_tc launch");
 }

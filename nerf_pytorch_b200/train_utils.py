@@ -26,16 +26,22 @@ from .nerf_helpers import Embedder, get_minibatches, ndc_rays
 # so validation renders use options.nerf.train.* for sampling/noise.  True reproduces that.
 COMPAT_MODE_QUIRK = True
 
-# 0: fp32 CUDA cores (default, bit-faithful fp32 arithmetic); 1: tcgen05 tensor cores (3xTF32)
-DEFAULT_IMPL = ops.IMPL_SIMT
+# None: tcgen05 tensor cores (3xTF32) wherever the kernels support the configuration (hidden 128, encodings
+# <= 64 wide, >= 16 samples per ray), fp32 CUDA cores otherwise; 0 / 1 force one implementation.
+DEFAULT_IMPL = None
+
+
+def _auto_impl(arch_c, arch_f, n_coarse, n_fine):
+    ok = all(a is None or (a.hidden == 128 and a.dim_xyz <= 64 and a.dim_dir <= 32) for a in (arch_c, arch_f))
+    return ops.IMPL_TC if ok and n_coarse >= 16 else ops.IMPL_SIMT
 
 # gradient synchronisation across ranks: (process_group, world_size) or None; see parallel.py
 _GRAD_SYNC = None
 
 
-def set_default_impl(impl: int):
+def set_default_impl(impl):
     global DEFAULT_IMPL
-    DEFAULT_IMPL = int(impl)
+    DEFAULT_IMPL = None if impl is None else int(impl)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -279,7 +285,11 @@ def predict_and_render_radiance(
 
     all_params = list(params_c) + list(params_f)
     training = torch.is_grad_enabled() and any(p.requires_grad for p in all_params)
-    cfg = (arch_c, arch_f, opts, blob_c, blob_f, training, DEFAULT_IMPL if impl is None else int(impl), len(params_c))
+    if impl is None:
+        impl = DEFAULT_IMPL
+    if impl is None:
+        impl = _auto_impl(arch_c, arch_f, nc, nf)
+    cfg = (arch_c, arch_f, opts, blob_c, blob_f, training, int(impl), len(params_c))
     out_c, out_f = _RenderChunk.apply(cfg, rays, t_vals, t_rand, noise_c, u, noise_f, *all_params)
     rgb_c, disp_c, acc_c = out_c[:, :3], out_c[:, 3], out_c[:, 4]
     if out_f is None:

@@ -125,10 +125,13 @@ def test_sample_pdf_indices_exact_given_cdf_and_values(name):
     assert (cdf2.cpu() - aux["cdf"]).abs().max() < 1e-6
     same = inds2.cpu().long() == aux["inds"]
     assert (~same).sum().item() <= max(2, inds2.numel() // 2000), (~same).sum().item()
-    # (u - cdf_below) / denom amplifies a 1-ulp cdf difference by up to 1/1e-5 inside a bin
-    assert ((zs2.cpu() - aux["z_samples"]).abs()[same]).max() < 5e-4
+    # the `denom < 1e-5 -> 1` switch itself is a discontinuity: a bin whose cdf step is within an ulp of
+    # 1e-5 lands on either side of it, which also moves a sample by up to one bin width at EQUAL index.
+    # So: (almost) all samples agree to fp32 resolution, none differs by more than a bin.
+    d = (zs2.cpu() - aux["z_samples"]).abs()
+    assert (d > 1e-4).double().mean().item() < 2e-3, (d > 1e-4).double().mean().item()
     bin_w = (aux["z_coarse"][:, 1:] - aux["z_coarse"][:, :-1]).max().item()
-    assert (zs2.cpu() - aux["z_samples"]).abs().max() <= 1.01 * bin_w
+    assert d.max() <= 1.01 * bin_w
     assert (z_fine2[:, 1:] >= z_fine2[:, :-1]).all()
 
 

@@ -82,3 +82,26 @@ def test_tc_end_to_end_against_reference_golden(name):
                                       encode_position_fn=epf, encode_direction_fn=edf, randoms=rnd, impl=1)
     for k in (0, 2, 3, 5):
         assert frac_close(out[k].cpu(), c.outputs[k], rtol=1e-4, atol=2e-5) > 0.97, k
+
+
+@pytest.mark.parametrize("name", TC_CASES)
+def test_tc_wgrad_matches_fp32_kernel(name):
+    """Weight gradients from the tcgen05 wgrad kernel (3xTF32) vs the fp32 CUDA-core kernel, same dY / stash."""
+    from nerf_pytorch_b200 import ops
+
+    c = Case(name)
+    rays, _, aux = c.aux()
+    arch = _arch(c)
+    blob = ops.pack_weights(arch, ops.flatten_state_dict(arch, c.sd_c, "cuda"))
+    z = aux["z_coarse"].cuda().contiguous()
+    gen = torch.Generator().manual_seed(11)
+    G = torch.randn(z.shape[0], z.shape[1], 4, generator=gen).cuda()
+    raw, stash = ops.mlp_fwd(arch, blob, rays.cuda(), z, want_stash=True)
+    g0, _ = ops.mlp_bwd(arch, blob, rays.cuda(), z, G, stash, impl=ops.IMPL_SIMT)
+    g1, _ = ops.mlp_bwd(arch, blob, rays.cuda(), z, G, stash, impl=ops.IMPL_TC)
+    torch.cuda.synchronize()
+    for lname, w_off, b_off, fin, fout in arch.flat_layout():
+        for off, n, what in ((w_off, fin * fout, "weight"), (b_off, fout, "bias")):
+            a, b = g0[off:off + n], g1[off:off + n]
+            scale = a.abs().max().item() + 1e-30
+            assert (a - b).abs().max().item() <= 1e-4 * scale, (lname, what, (a - b).abs().max().item(), scale)

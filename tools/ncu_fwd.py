@@ -21,5 +21,5 @@ for _ in range(3):
 G = torch.randn_like(raw)
 if os.environ.get("BWD", "1") == "1":
     for _ in range(2):
-        ops.mlp_bwd(arch, blob, rays, z, G, stash)
+        ops.mlp_bwd(arch, blob, rays, z, G, stash, impl=impl)
 torch.cuda.synchronize()

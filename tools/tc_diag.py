@@ -54,3 +54,29 @@ for archname, kw in (("A0", dict(num_layers=4, hidden=128, skip_every=4)), ("A1"
             print(f"{archname} S={S} impl={impl}: {t:.3f} ms ({2*macs*N*S/t/1e9:.1f} TFLOP/s useful), with stash {ts:.3f} ms", flush=True)
         r0 = ops.mlp_fwd(arch, blob, rays, z, impl=0); r1 = ops.mlp_fwd(arch, blob, rays, z, impl=1)
         print("   max diff", (r0-r1).abs().max().item(), "scale", r0.abs().max().item())
+
+# cycle breakdown of the tcgen05 kernel (epilogue thread 0 of every CTA)
+import ctypes
+from nerf_pytorch_b200 import _lib
+prof = torch.zeros(148 * 4, dtype=torch.int64, device="cuda")
+_lib.load().nerfb200_debug_tc_profile(ctypes.c_void_p(prof.data_ptr()))
+arch = ops.ArchSpec(n_freq_xyz=10, n_freq_dir=4, num_layers=4, hidden=128, skip_every=4)
+blob = ops.pack_weights(arch, torch.randn(arch.flat_param_count(), device="cuda") * 0.05)
+z = torch.sort(torch.rand(N, 192, device="cuda") * 4 + 2, -1).values.contiguous()
+ops.mlp_fwd(arch, blob, rays, z, impl=1); torch.cuda.synchronize()
+pr = prof.view(148, 4).double()
+print("A0 S=192 per-CTA cycles: prologue %.0f  wait-mma %.0f  epilogue %.0f  total %.0f (tiles/CTA %.1f)" % (*pr.mean(0).tolist(), 4096*192/128/148))
+_lib.load().nerfb200_debug_tc_profile(None)
+
+# backward timing: SIMT vs (SIMT dgrad + TC wgrad)
+for archname, kw in (("A0", dict(num_layers=4, hidden=128, skip_every=4)), ("A1", dict(num_layers=8, hidden=128, skip_every=3))):
+    arch = ops.ArchSpec(n_freq_xyz=10, n_freq_dir=4, **kw)
+    blob = ops.pack_weights(arch, torch.randn(arch.flat_param_count(), device="cuda") * 0.05)
+    z = torch.sort(torch.rand(N, 192, device="cuda") * 4 + 2, -1).values.contiguous()
+    raw, stash = ops.mlp_fwd(arch, blob, rays, z, impl=1, want_stash=True)
+    G = torch.randn_like(raw)
+    for impl in (0, 1):
+        t = timeit(lambda: ops.mlp_bwd(arch, blob, rays, z, G, stash, impl=impl), n=5, warm=2)
+        print(f"{archname} S=192 mlp_bwd impl={impl}: {t:.3f} ms", flush=True)
+    g0, _ = ops.mlp_bwd(arch, blob, rays, z, G, stash, impl=0); g1, _ = ops.mlp_bwd(arch, blob, rays, z, G, stash, impl=1)
+    print("   grad max diff", (g0-g1).abs().max().item(), "scale", g0.abs().max().item())

@@ -93,6 +93,8 @@ int build_plan(const nerfb200_arch_t* a, Plan* p) {
     g.k_tc = enc_sel == 1 ? k_h : k_h + g.k_enc;
     g.tc_off = blob;
     blob += 2 * g.k_tc * n;  // hi + lo copies
+    g.tcd_off = blob;
+    blob += 2 * g.k_h * n;
     g.cum_n = cum;
     cum += n;
     g.flat_w = flat;

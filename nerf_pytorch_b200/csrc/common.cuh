@@ -36,6 +36,8 @@ struct GemmLayer {
   // no swizzle: 8-row core matrices 128 B apart, the two K halves one slab apart).
   int k_tc;
   int tc_off;
+  // dgrad operand copy: Wt[k < k_h][n] as K-major slabs over the reduction index n, hi|lo per 8 n
+  int tcd_off;
 };
 
 struct HeadLayer {
@@ -81,6 +83,8 @@ int launch_mlp_fwd_simt(const Plan& p, const float* blob, const float* rays, int
 int launch_mlp_bwd(const Plan& p, const float* blob, const float* rays, int ray_stride, const float* z,
                    int64_t n_rays, int n_samples, const float* d_raw, const float* stash, float* gstash,
                    float* flat_grad, int impl, cudaStream_t s);
+int launch_dgrad_tc(const Plan& p, const float* blob, const float* d_raw, const float* stash, float* gstash,
+                    int64_t P, cudaStream_t s);
 int launch_wgrad_tc(const Plan& p, const float* rays, int ray_stride, const float* z, int64_t n_rays, int n_samples,
                     const float* stash, const float* gstash, float* flat_grad, cudaStream_t s);
 int launch_composite_fwd(const float* raw, const float* z, const float* rays, int ray_stride, const float* noise,

@@ -360,4 +360,221 @@ int launch_mlp_fwd_tc(const Plan& p, const float* blob, const float* rays, int r
   return check_cuda(cudaGetLastError(), "mlp_fwd_tc launch");
 }
 
+
+
+// =============================================================================================
+// backward, tensor-core dgrad chain: for one 128-point tile walk the layers in reverse,
+//     G_t = ( G_s * W_s[:, :hidden]  +  d_raw * W_head ) (.) [stash_t > 0]          (s = consumer of t)
+// with G_s resident in tensor memory as the A operand (hi/lo), the transposed weights streamed through
+// the same bulk-copy ring as the forward, and every G_t written to `gstash` for the wgrad kernel.
+// =============================================================================================
+namespace tcd {
+struct SmemD {
+  static constexpr int ring = 0;                                     // kStages x 8 KB
+  static constexpr int headw = ring + tc::kStages * tc::kStageBytes;  // head weights (4*128 + 3*64 floats)
+  static constexpr int bars = headw + (4 * 128 + 3 * 64 + 16) * 4;
+  static constexpr int total = bars + 256;
+};
+}  // namespace tcd
+
+__global__ void __launch_bounds__(kThreadsTc, 1)
+mlp_dgrad_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob, const float* __restrict__ d_raw,
+                    const float* __restrict__ stash, float* __restrict__ gstash, int64_t P, int64_t n_tiles) {
+  using tcd::SmemD;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  float* s_headw = reinterpret_cast<float*>(sm + SmemD::headw);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + SmemD::bars);
+  uint64_t* bar_full = bars;
+  uint64_t* bar_empty = bars + kStages;
+  uint64_t* bar_a = bars + 2 * kStages;
+  uint64_t* bar_acc = bars + 2 * kStages + 1;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 2);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&bar_full[i], 1);
+      mbar_init(&bar_empty[i], 1);
+    }
+    mbar_init(bar_a, kEpiThreads);
+    mbar_init(bar_acc, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)),
+                 "r"(kTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  const int hw1 = p.h[0].n_out * p.h[0].k;
+  const int hw2 = p.n_head > 1 ? p.h[1].n_out * p.h[1].k : 0;
+  for (int i = tid; i < hw1; i += kThreadsTc) s_headw[i] = blob[p.h[0].w_off + i];
+  for (int i = tid; i < hw2; i += kThreadsTc) s_headw[hw1 + i] = blob[p.h[1].w_off + i];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *s_tmem;
+  const int64_t my_tiles = (n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+  // consumer gemm of layer t (the layer whose h-input is t's output), or -1
+  auto consumer = [&](int t) {
+    int s = -1;
+    for (int c = t + 1; c < p.n_gemm; ++c)
+      if (p.g[c].src == t) s = c;
+    return s;
+  };
+
+  if (warp == 5) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int64_t it = 0; it < my_tiles; ++it) {
+        for (int t = p.n_gemm - 1; t >= 0; --t) {
+          const int s = consumer(t);
+          if (s < 0) continue;
+          const GemmLayer& g = p.g[s];
+          const uint32_t bytes = 64u * g.k_h;
+          const uint8_t* src = reinterpret_cast<const uint8_t*>(blob + g.tcd_off);
+          const int ksteps = g.n >> 3;
+          for (int ks = 0; ks < ksteps; ++ks) {
+            mbar_wait(&bar_empty[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&bar_full[stage], bytes);
+            bulk_g2s(sm + SmemD::ring + stage * kStageBytes, src + (size_t)ks * bytes, bytes, &bar_full[stage]);
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 4) {
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, a_phase = 0;
+      for (int64_t it = 0; it < my_tiles; ++it) {
+        for (int t = p.n_gemm - 1; t >= 0; --t) {
+          const int s = consumer(t);
+          if (s < 0) continue;
+          const GemmLayer& g = p.g[s];
+          const uint32_t idesc = make_idesc(g.k_h);
+          const uint32_t slab_b = 16u * g.k_h;
+          const int ksteps = g.n >> 3;
+          mbar_wait(bar_a, a_phase);
+          a_phase ^= 1;
+          tc_fence_after();
+          for (int ks = 0; ks < ksteps; ++ks) {
+            mbar_wait(&bar_full[stage], phase);
+            tc_fence_after();
+            const uint32_t wb = smem_u32(sm + SmemD::ring + stage * kStageBytes);
+            const uint64_t b_hi = make_desc(wb, slab_b, 128);
+            const uint64_t b_lo = make_desc(wb + 2 * slab_b, slab_b, 128);
+            const uint32_t a_hi = tmem + kColAhi + 8 * ks, a_lo = tmem + kColAlo + 8 * ks;
+            mma_ts(tmem + kColAcc, a_hi, b_hi, idesc, ks > 0 ? 1u : 0u);
+            mma_ts(tmem + kColAcc, a_lo, b_hi, idesc, 1u);
+            mma_ts(tmem + kColAcc, a_hi, b_lo, idesc, 1u);
+            mma_commit(&bar_empty[stage]);
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
+          mma_commit(bar_acc);
+        }
+      }
+    }
+  } else {
+    const int row = tid;
+    const uint32_t lane_base = ((uint32_t)(warp * 32)) << 16;
+    uint32_t acc_phase = 0;
+    for (int64_t it = 0; it < my_tiles; ++it) {
+      const int64_t tile = blockIdx.x + it * gridDim.x;
+      const int64_t pt = tile * kTileRows + row;
+      const bool valid = pt < P;
+      const float4 dr4 = valid ? reinterpret_cast<const float4*>(d_raw)[pt] : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float dr[4] = {dr4.x, dr4.y, dr4.z, dr4.w};
+      for (int t = p.n_gemm - 1; t >= 0; --t) {
+        const GemmLayer& gt = p.g[t];
+        const int s = consumer(t);
+        int hsel = -1;
+        for (int c = 0; c < p.n_head; ++c)
+          if (p.h[c].src == t) hsel = c;
+        const float* hw = hsel == 1 ? s_headw + hw1 : s_headw;
+        const int hk = hsel >= 0 ? p.h[hsel].k : 0, hn = hsel >= 0 ? p.h[hsel].n_out : 0;
+        const int hcol = hsel >= 0 ? p.h[hsel].out_col : 0;
+        const float* st = stash + (size_t)P * gt.cum_n + (size_t)(valid ? pt : 0) * gt.n;
+        float* gs = gstash + (size_t)P * gt.cum_n + (size_t)(valid ? pt : 0) * gt.n;
+        if (s >= 0) {
+          mbar_wait(bar_acc, acc_phase);
+          acc_phase ^= 1;
+          tc_fence_after();
+        }
+        for (int c0 = 0; c0 < gt.n; c0 += 32) {
+          uint32_t v[32];
+          if (s >= 0) {
+            tmem_ld32(tmem + lane_base + kColAcc + c0, v);
+            tmem_wait_ld();
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0u;
+          }
+          uint32_t hi[32], lo[32];
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float x[4] = {__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                          __uint_as_float(v[j + 3])};
+            if (hsel >= 0) {
+#pragma unroll
+              for (int c = 0; c < 4; ++c)
+                if (c < hn) {
+                  const float4 w = *reinterpret_cast<const float4*>(hw + c * hk + c0 + j);
+                  const float d = dr[(hcol + c) & 3];
+                  x[0] = fmaf(d, w.x, x[0]); x[1] = fmaf(d, w.y, x[1]); x[2] = fmaf(d, w.z, x[2]); x[3] = fmaf(d, w.w, x[3]);
+                }
+            }
+            if (gt.relu) {
+              const float4 a = valid ? __ldg(reinterpret_cast<const float4*>(st + c0 + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+              x[0] = a.x > 0.f ? x[0] : 0.f; x[1] = a.y > 0.f ? x[1] : 0.f;
+              x[2] = a.z > 0.f ? x[2] : 0.f; x[3] = a.w > 0.f ? x[3] : 0.f;
+            }
+            if (valid) *reinterpret_cast<float4*>(gs + c0 + j) = make_float4(x[0], x[1], x[2], x[3]);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              hi[j + q] = tf32_hi(x[q]);
+              lo[j + q] = __float_as_uint(x[q] - __uint_as_float(hi[j + q]));
+            }
+          }
+          if (t > 0) {
+            tmem_st32(tmem + lane_base + kColAhi + c0, hi);
+            tmem_st32(tmem + lane_base + kColAlo + c0, lo);
+          }
+        }
+        if (t > 0) {
+          tmem_wait_st();
+          tc_fence_before();
+          mbar_arrive(bar_a);
+        } else {
+          tc_fence_before();
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols));
+}
+
+int launch_dgrad_tc(const Plan& p, const float* blob, const float* d_raw, const float* stash, float* gstash, int64_t P,
+                    cudaStream_t s) {
+  if (p.hidden != 128) {
+    set_error("dgrad impl=1 (tcgen05): hidden_size %d not supported (128 only)", p.hidden);
+    return NERFB200_ERR_UNSUPPORTED;
+  }
+  const int64_t tiles = (P + kTileRows - 1) / kTileRows;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = (int)(tiles < sms ? tiles : sms);
+  const size_t bytes = tcd::SmemD::total + 1024;
+  int rc = check_cuda(cudaFuncSetAttribute(mlp_dgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes),
+                      "dgrad_tc smem attribute");
+  if (rc) return rc;
+  mlp_dgrad_tc_kernel<<<grid, kThreadsTc, bytes, s>>>(p, blob, d_raw, stash, gstash, P, tiles);
+  count_launch();
+  return check_cuda(cudaGetLastError(), "dgrad_tc launch");
+}
+
 }  // namespace nerfb200

@@ -235,6 +235,21 @@ __global__ void pack_kernel(Plan p, const float* __restrict__ flat, float* __res
         const float hi = __uint_as_float(hb);
         val = part == 0 ? hi : w - hi;
         found = true;
+      } else if (idx >= g.tcd_off && idx < g.tcd_off + 2 * g.k_h * g.n) {
+        // dgrad operand: [kstep over n][hi|lo][slab 0|1][k < k_h][4]: element (k, n = kstep*8 + slab*4 + j) = W[n][k]
+        const int e = idx - g.tcd_off;
+        const int per_step = 16 * g.k_h;
+        const int ks = e / per_step, r = e - ks * per_step;
+        const int part = r / (8 * g.k_h), r2 = r - part * 8 * g.k_h;
+        const int slab = r2 / (4 * g.k_h), r3 = r2 - slab * 4 * g.k_h;
+        const int k = r3 >> 2, j = r3 & 3;
+        const int nn = ks * 8 + slab * 4 + j;
+        const float w = flat[g.flat_w + nn * in_real + k];
+        uint32_t hb;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(w));
+        const float hi = __uint_as_float(hb);
+        val = part == 0 ? hi : w - hi;
+        found = true;
       }
     }
     for (int hi = 0; hi < p.n_head && !found; ++hi) {

@@ -97,9 +97,13 @@ def test_tc_wgrad_matches_fp32_kernel(name):
     gen = torch.Generator().manual_seed(11)
     G = torch.randn(z.shape[0], z.shape[1], 4, generator=gen).cuda()
     raw, stash = ops.mlp_fwd(arch, blob, rays.cuda(), z, want_stash=True)
-    g0, _ = ops.mlp_bwd(arch, blob, rays.cuda(), z, G, stash, impl=ops.IMPL_SIMT)
-    g1, _ = ops.mlp_bwd(arch, blob, rays.cuda(), z, G, stash, impl=ops.IMPL_TC)
+    g0, gs0 = ops.mlp_bwd(arch, blob, rays.cuda(), z, G, stash, impl=ops.IMPL_SIMT)
+    g1, gs1 = ops.mlp_bwd(arch, blob, rays.cuda(), z, G, stash, impl=ops.IMPL_TC)
     torch.cuda.synchronize()
+    # dgrad chain (tcgen05) vs fp32 kernel: per-layer pre-activation gradients
+    n_act = sum(o for _, _, _, _, o in arch.flat_layout() if o >= 64) * z.numel()
+    gscale = gs0[:n_act].abs().max().item()
+    assert (gs1[:n_act] - gs0[:n_act]).abs().max().item() <= 1e-4 * gscale, ((gs1[:n_act] - gs0[:n_act]).abs().max().item(), gscale)
     for lname, w_off, b_off, fin, fout in arch.flat_layout():
         for off, n, what in ((w_off, fin * fout, "weight"), (b_off, fout, "bias")):
             a, b = g0[off:off + n], g1[off:off + n]

@@ -120,6 +120,21 @@ def measured_peaks():
 # ------------------------------------------------------------------------------------------------
 # reference arm / CPU baseline: the oracle port timed on the host cores
 # ------------------------------------------------------------------------------------------------
+def best_cpu_threads(arch):
+    """The reference is timed with the thread count that serves IT best: torch's intra-op pool does not scale
+    to 100+ threads on these small ops (measured: 128 threads are ~20x slower than 16), so probe a few."""
+    cores = os.cpu_count() or 1
+    cands = sorted({c for c in (8, 16, 32, 64, cores) if c <= cores})
+    best, best_t = cands[0], float("inf")
+    for c in cands:
+        t = cpu_train_steps(arch, 128, steps=1, warmup=1, threads=c)[0]
+        if t < best_t:
+            best, best_t = c, t
+        if t > 3 * best_t:
+            break
+    return best
+
+
 def cpu_train_steps(arch, n_rays, steps, warmup, threads=None):
     """fwd + loss + backward + Adam of the reference algorithm on CPU (oracle/nerf_oracle.py).  Returns s/step list."""
     from oracle import nerf_oracle as O
@@ -153,12 +168,12 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return  # rank 0 alone runs the CPU arm
-    cores = os.cpu_count() or 1
     n_sample = 512
-    times = cpu_train_steps(args.arch, n_sample, args.steps, args.warmup, threads=cores)
+    times = cpu_train_steps(args.arch, n_sample, args.steps, args.warmup, threads=best_cpu_threads(args.arch))
     ms = 1e3 * sum(times) / len(times)
     value = n_sample / (ms / 1e3)
-    sample = f"{n_sample} of the {RAYS_PER_GPU} rays per step (same sampler/model/loss/Adam), {args.steps} steps"
+    sample = (f"{n_sample} of the {RAYS_PER_GPU} rays per step (same sampler/model/loss/Adam), {args.steps} steps; "
+              f"thread count = best of a probe over 8..{os.cpu_count()} host threads")
     line = {
         "impl": "reference", "metric": "rays/sec (4096 rays, 64c+128f samples), train step", "value": value,
         "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
@@ -317,11 +332,11 @@ def run_ours(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         n_sample = 512
-        times = cpu_train_steps(args.arch, n_sample, steps=3, warmup=1, threads=os.cpu_count())
+        times = cpu_train_steps(args.arch, n_sample, steps=3, warmup=1, threads=best_cpu_threads(args.arch))
         v = n_sample / (sum(times) / len(times))
         cpu = {"value": v, "unit": "rays/s", "cores": torch.get_num_threads(), "kind": "port",
                "sample": f"{n_sample} of the {RAYS_PER_GPU} rays per step, 3 timed steps after 1 warm-up (oracle port of "
-                         "the reference ops, torch CPU, all host threads)"}
+                         f"the reference ops, torch CPU; thread count = best of a probe over 8..{os.cpu_count()} host threads)"}
 
     if rank == 0:
         line = {

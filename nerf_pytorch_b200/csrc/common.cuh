@@ -86,7 +86,7 @@ int launch_mlp_bwd(const Plan& p, const float* blob, const float* rays, int ray_
 int launch_dgrad_tc(const Plan& p, const float* blob, const float* d_raw, const float* stash, float* gstash,
                     int64_t P, cudaStream_t s);
 int launch_wgrad_tc(const Plan& p, const float* rays, int ray_stride, const float* z, int64_t n_rays, int n_samples,
-                    const float* stash, const float* gstash, float* flat_grad, cudaStream_t s);
+                    const float* stash, const float* gstash, const float* d_raw, float* flat_grad, cudaStream_t s);
 int launch_composite_fwd(const float* raw, const float* z, const float* rays, int ray_stride, const float* noise,
                          int64_t n_rays, int n_samples, float noise_std, int white_bkgd, float* out,
                          float* weights, cudaStream_t s);

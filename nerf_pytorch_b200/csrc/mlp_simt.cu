@@ -644,11 +644,7 @@ int launch_mlp_bwd(const Plan& p, const float* blob, const float* rays, int ray_
   if (rc) return rc;
   const int items = wg_item_count(p);
   if (impl == 1 && p.hidden == 128) {
-    // tensor cores for every GEMM-shaped item, CUDA cores for the 1..4-row heads
-    rc = launch_wgrad_tc(p, rays, ray_stride, z, n_rays, n_samples, stash, gstash, flat_grad, s);
-    if (rc) return rc;
-    return launch_wgrad_simt(p, rays, ray_stride, z, n_samples, d_raw, stash, gstash, P, flat_grad,
-                             items - p.n_head, p.n_head, s);
+    return launch_wgrad_tc(p, rays, ray_stride, z, n_rays, n_samples, stash, gstash, d_raw, flat_grad, s);
   }
   return launch_wgrad_simt(p, rays, ray_stride, z, n_samples, d_raw, stash, gstash, P, flat_grad, 0, items, s);
 }

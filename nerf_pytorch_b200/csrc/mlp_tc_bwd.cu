@@ -42,7 +42,8 @@ __device__ __forceinline__ void split_store(uint8_t* hi_base, uint8_t* lo_base, 
 __global__ void __launch_bounds__(kThreadsW, 1)
 mlp_wgrad_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ rays, int ray_stride,
                     const float* __restrict__ z, int S, const float* __restrict__ stash,
-                    const float* __restrict__ gstash, int64_t P, float* __restrict__ flat_grad, int n_items) {
+                    const float* __restrict__ gstash, const float* __restrict__ d_raw, int64_t P,
+                    float* __restrict__ flat_grad, int n_items) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + kStagesW * kStageBytesW);
@@ -54,8 +55,12 @@ mlp_wgrad_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ ra
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if ((int)blockIdx.y >= n_items) return;
   const WgItem it = wg_decode(p, blockIdx.y);
-  if (it.kind == 2) return;  // narrow heads stay on the CUDA-core kernel
-  const GemmLayer& g = p.g[it.t];
+  // operand sources.  gemm items: A rows = dY_t (gstash), B rows = the producing layer's output or the stashed
+  // encoding.  Head items (fc_alpha / fc_rgb / fc_out): A rows = d_raw[p][0..3] masked to the head's columns
+  // (4 live rows of the 128-row tile), B rows = the output of the layer the head reads.
+  const bool head = it.kind == 2;
+  const GemmLayer& g = p.g[head ? p.h[it.t].src : it.t];
+  const int hcol0 = head ? p.h[it.t].out_col : 0, hcols = head ? p.h[it.t].n_out : 0;
 
   // contiguous point range of this CTA, in units of one stage
   const int64_t stages_total = (P + kStagePts - 1) / kStagePts;
@@ -98,12 +103,19 @@ mlp_wgrad_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ ra
     const bool is_a = warp < 4;
     const int quad0 = warp & 3;       // this thread transposes quads quad0 and quad0 + 4 of every stage
     // X rows: the producing layer's stashed output (kind 0) or the stashed, zero-padded encoding (kind 1)
-    const int xw = it.kind == 0 ? p.g[g.src].n : (g.enc_sel ? p.dim_dir_pad : p.dim_xyz_pad);
-    const bool on = is_a ? (4 * c < it.nblk) : (4 * c < it.kblk && 4 * c < xw);
-    const float* src = is_a ? gstash + (size_t)P * g.cum_n + it.n0 + 4 * c
-                            : (it.kind == 0 ? stash + (size_t)P * p.g[g.src].cum_n + it.k0 + 4 * c
-                                            : stash + (size_t)P * p.enc_cum[g.enc_sel] + 4 * c);
-    const int ld = is_a ? g.n : xw;
+    const int xw = head ? g.n : (it.kind == 0 ? p.g[g.src].n : (g.enc_sel ? p.dim_dir_pad : p.dim_xyz_pad));
+    const bool on = is_a ? (head ? c == 0 : 4 * c < it.nblk) : (4 * c < it.kblk && 4 * c < xw);
+    const float* src =
+        is_a ? (head ? d_raw : gstash + (size_t)P * g.cum_n + it.n0 + 4 * c)
+             : (head ? stash + (size_t)P * g.cum_n + 4 * c
+                     : (it.kind == 0 ? stash + (size_t)P * p.g[g.src].cum_n + it.k0 + 4 * c
+                                     : stash + (size_t)P * p.enc_cum[g.enc_sel] + 4 * c));
+    const int ld = is_a ? (head ? 4 : g.n) : xw;
+    // head items: keep only this head's columns of d_raw
+    const float hm0 = (!head || (hcol0 <= 0 && 0 < hcol0 + hcols)) ? 1.f : 0.f;
+    const float hm1 = (!head || (hcol0 <= 1 && 1 < hcol0 + hcols)) ? 1.f : 0.f;
+    const float hm2 = (!head || (hcol0 <= 2 && 2 < hcol0 + hcols)) ? 1.f : 0.f;
+    const float hm3 = (!head || (hcol0 <= 3 && 3 < hcol0 + hcols)) ? 1.f : 0.f;
     float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
     uint32_t stage = 0, phase = 0;
@@ -115,7 +127,9 @@ mlp_wgrad_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ ra
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int64_t pt = q0 + 4 * (quad0 + 4 * h) + i;
-          v[4 * h + i] = (on && pt < pt_end) ? __ldg(reinterpret_cast<const float4*>(src + (size_t)pt * ld)) : zero4;
+          float4 t4 = (on && pt < pt_end) ? __ldg(reinterpret_cast<const float4*>(src + (size_t)pt * ld)) : zero4;
+          if (head && is_a) { t4.x *= hm0; t4.y *= hm1; t4.z *= hm2; t4.w *= hm3; }
+          v[4 * h + i] = t4;
         }
     };
     issue_loads(pt_begin, cur);
@@ -150,18 +164,28 @@ mlp_wgrad_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ ra
       for (int j = 0; j < 8; ++j) cur[j] = nxt[j];
     }
     if (it.bias && is_a && on) {
-      float* gb = flat_grad + g.flat_b + it.n0 + 4 * c;
-      atomicAdd(gb + 0, bsum.x); atomicAdd(gb + 1, bsum.y); atomicAdd(gb + 2, bsum.z); atomicAdd(gb + 3, bsum.w);
+      if (head) {
+        float* gb = flat_grad + p.h[it.t].flat_b - hcol0;
+        const float bs[4] = {bsum.x, bsum.y, bsum.z, bsum.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (i >= hcol0 && i < hcol0 + hcols) atomicAdd(gb + i, bs[i]);
+      } else {
+        float* gb = flat_grad + g.flat_b + it.n0 + 4 * c;
+        atomicAdd(gb + 0, bsum.x); atomicAdd(gb + 1, bsum.y); atomicAdd(gb + 2, bsum.z); atomicAdd(gb + 3, bsum.w);
+      }
     }
     // ===================== drain the accumulator (warps 0-3: TMEM lane = output row n) =====================
     if (warp < 4) {
       mbar_wait(bar_done, 0);
       tc_fence_after();
       const int row = tid;
-      const int in_real = g.k_h + g.enc_real;
-      const int coff = it.kind == 0 ? it.k0 : g.k_h;
-      const int kreal = it.kind == 0 ? it.kblk : g.enc_real;
-      float* dst = flat_grad + g.flat_w + (size_t)(it.n0 + row) * in_real + coff;
+      const int in_real = head ? p.h[it.t].k : g.k_h + g.enc_real;
+      const int coff = head ? 0 : (it.kind == 0 ? it.k0 : g.k_h);
+      const int kreal = head ? p.h[it.t].k : (it.kind == 0 ? it.kblk : g.enc_real);
+      const bool row_live = head ? (row >= hcol0 && row < hcol0 + hcols) : (row < it.nblk);
+      float* dst = head ? flat_grad + p.h[it.t].flat_w + (size_t)(row - hcol0) * in_real
+                        : flat_grad + g.flat_w + (size_t)(it.n0 + row) * in_real + coff;
       for (int c0 = 0; c0 < n_mma; c0 += 32) {
         uint32_t v[32];
         if (n_mma - c0 >= 32) {
@@ -179,7 +203,7 @@ mlp_wgrad_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ ra
           for (int j = 16; j < 32; ++j) v[j] = 0u;
         }
         tmem_wait_ld();
-        if (row < it.nblk) {
+        if (row_live) {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
             if (c0 + j < kreal) atomicAdd(dst + c0 + j, __uint_as_float(v[j]));
@@ -219,13 +243,13 @@ mlp_wgrad_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ ra
 }
 
 int launch_wgrad_tc(const Plan& p, const float* rays, int ray_stride, const float* z, int64_t n_rays, int n_samples,
-                    const float* stash, const float* gstash, float* flat_grad, cudaStream_t s) {
+                    const float* stash, const float* gstash, const float* d_raw, float* flat_grad, cudaStream_t s) {
   if (p.hidden != 128) {
     set_error("wgrad impl=1 (tcgen05): hidden_size %d not supported (128 only)", p.hidden);
     return NERFB200_ERR_UNSUPPORTED;
   }
   const int64_t P = n_rays * n_samples;
-  const int items = wg_item_count(p) - p.n_head;  // gemm items come first in the item order
+  const int items = wg_item_count(p);
   const size_t bytes = (size_t)kStagesW * kStageBytesW + 256 + 1024;
   int rc = check_cuda(cudaFuncSetAttribute(mlp_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes),
                       "wgrad_tc smem attribute");
@@ -238,8 +262,8 @@ int launch_wgrad_tc(const Plan& p, const float* rays, int ray_stride, const floa
   if (split > stages) split = (int)stages;
   if (split < 1) split = 1;
   dim3 grid(split, items);
-  mlp_wgrad_tc_kernel<<<grid, kThreadsW, bytes, s>>>(p, rays, ray_stride, z, n_samples, stash, gstash, P, flat_grad,
-                                                     items);
+  mlp_wgrad_tc_kernel<<<grid, kThreadsW, bytes, s>>>(p, rays, ray_stride, z, n_samples, stash, gstash, d_raw, P,
+                                                     flat_grad, items);
   count_launch();
   return check_cuda(cudaGetLastError(), "wgrad_tc launch");
 }

@@ -142,6 +142,13 @@ int build_plan(const nerfb200_arch_t* a, Plan* p) {
   cum += p->dim_xyz_pad;
   p->enc_cum[1] = cum;
   cum += p->dim_dir_pad;
+  p->mask_base = cum;
+  int mw = 0;
+  for (int i = 0; i < ng; ++i) {
+    p->g[i].mask_cum = mw;
+    mw += p->g[i].n / 32;
+  }
+  cum += mw;
   p->sum_n = cum;
   p->blob_floats = blob;
   p->flat_floats = flat;

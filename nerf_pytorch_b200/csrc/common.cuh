@@ -38,6 +38,7 @@ struct GemmLayer {
   int tc_off;
   // dgrad operand copy: Wt[k < k_h][n] as K-major slabs over the reduction index n, hi|lo per 8 n
   int tcd_off;
+  int mask_cum;  // ReLU bit-mask words (uint32, one bit per output) per point before this layer's
 };
 
 struct HeadLayer {
@@ -57,6 +58,7 @@ struct Plan {
   int hidden;
   int sum_n;  // floats stashed per point: every gemm layer's output + the two padded encodings
   int enc_cum[2];  // stash slice of the xyz / direction encoding: base + n_points * enc_cum[sel], width dim_*_pad
+  int mask_base;   // stash slice of the ReLU bit masks: base + n_points * (mask_base + g.mask_cum), n/32 words per point
   int dim_xyz, dim_xyz_pad, dim_dir, dim_dir_pad;
   int n_freq_xyz, n_freq_dir, inc_xyz, inc_dir;
   int blob_floats, flat_floats;

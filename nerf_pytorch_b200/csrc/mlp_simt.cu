@@ -259,6 +259,21 @@ mlp_fwd_simt_kernel(const __grid_constant__ Plan p, const FwdSmem sm, const floa
         }
       }
       __syncthreads();
+      if (stash && tid < kTileRows && p0 + tid < P) {
+        // ReLU bit mask of this row (read by the tcgen05 dgrad kernel): bit c = output c > 0
+        uint32_t* mk = reinterpret_cast<uint32_t*>(stash) + (size_t)P * (p.mask_base + g.mask_cum) +
+                       (size_t)(p0 + tid) * (g.n / 32);
+        for (int w = 0; w < g.n / 32; ++w) {
+          uint32_t bits = 0;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 a = *reinterpret_cast<const float4*>(act + tid * sm.act_ld + 32 * w + 4 * q);
+            bits |= (a.x > 0.f ? 1u : 0u) << (4 * q) | (a.y > 0.f ? 1u : 0u) << (4 * q + 1) |
+                    (a.z > 0.f ? 1u : 0u) << (4 * q + 2) | (a.w > 0.f ? 1u : 0u) << (4 * q + 3);
+          }
+          mk[w] = bits;
+        }
+      }
     };
 
     if (g.n == 64 * NJH) {

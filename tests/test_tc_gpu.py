@@ -34,9 +34,16 @@ def test_tc_forward_matches_simt_and_oracle(name):
         e_simt = (raw0.cpu().double() - want.double()).abs().max().item()
         assert e_tc <= 1e-4 * scale + 1e-5, (tag, e_tc, e_simt, scale)
         assert frac_close(raw1.cpu(), want, rtol=1e-4, atol=1e-5 * max(1.0, scale)) > 0.999, tag
-        # hidden activations (the stash the backward consumes) agree with the fp32 kernel's
-        s_scale = st0.abs().max().item()
-        assert (st1 - st0).abs().max().item() <= 1e-4 * s_scale + 1e-6, (tag, (st1 - st0).abs().max().item(), s_scale)
+        # hidden activations + encodings (the stash the backward consumes) agree with the fp32 kernel's,
+        # and the ReLU bit masks (last section of the stash) agree except where an activation is ~0
+        P = z.numel()
+        mask_words = sum(o // 32 for _, _, _, _, o in arch.flat_layout() if o >= 64)
+        n_float = st0.numel() - P * mask_words
+        s_scale = st0[:n_float].abs().max().item()
+        assert (st1[:n_float] - st0[:n_float]).abs().max().item() <= 1e-4 * s_scale + 1e-6, tag
+        m0, m1 = st0[n_float:].view(torch.int32), st1[n_float:].view(torch.int32)
+        flips = (m0 ^ m1).ne(0).float().mean().item()
+        assert flips < 1e-3, (tag, flips)
 
 
 def test_tc_ragged_tail_and_sizes():

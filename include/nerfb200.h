@@ -68,6 +68,8 @@ int64_t nerfb200_launch_count(void);
 /* debug hook: device buffer of 4 int64 per CTA receiving the tcgen05 kernel's cycle counters
  * [prologue, wait-for-MMA, epilogue, total] of its epilogue thread 0; NULL switches it off. */
 void nerfb200_debug_tc_profile(void* buf);
+/* debug hook for timing experiments (results are garbage): bit 0 skips the weight copies, bit 1 the MMAs */
+void nerfb200_debug_tc_flags(int32_t flags);
 
 /* ---- parameters -------------------------------------------------------------------------------
  * Canonical order of the linears ("slots"): layer1, layers_xyz[0..num_layers-2], then

@@ -248,6 +248,7 @@ int32_t nerfb200_version(void) { return NERFB200_VERSION; }
 const char* nerfb200_last_error(void) { return g_err; }
 int64_t nerfb200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 void nerfb200_debug_tc_profile(void* buf) { set_tc_profile(buf); }
+void nerfb200_debug_tc_flags(int32_t flags) { set_tc_flags(flags); }
 
 int64_t nerfb200_num_linear(const nerfb200_arch_t* arch) {
   Plan p;

@@ -102,6 +102,7 @@ int launch_adam(float* p, const float* g, float* m, float* v, int64_t n, int ste
                 float eps, float grad_scale, cudaStream_t s);
 // tcgen05 path (mlp_tc.cu)
 void set_tc_profile(void* p);
+void set_tc_flags(int f);
 int launch_mlp_fwd_tc(const Plan& p, const float* blob, const float* rays, int ray_stride, const float* z,
                       int64_t n_rays, int n_samples, float* raw, float* stash, cudaStream_t s);
 

@@ -27,6 +27,8 @@ namespace nerfb200 {
 
 static long long* g_tc_prof = nullptr;  // debug hook: per-CTA cycle counters (nerfb200_debug_tc_profile)
 void set_tc_profile(void* p) { g_tc_prof = static_cast<long long*>(p); }
+static int g_tc_flags = 0;  // debug: 1 = skip the weight copies, 2 = skip the MMAs (timing experiments only)
+void set_tc_flags(int f) { g_tc_flags = f; }
 
 namespace tc {
 constexpr int kEpiThreads = 256;
@@ -100,7 +102,7 @@ mlp_chain_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ bl
                     float* __restrict__ raw,          // fwd: out [P][4];   dgrad: d_raw in (read only)
                     float* __restrict__ stash,        // fwd: out or NULL;  dgrad: in
                     float* __restrict__ gstash,       // dgrad: out
-                    long long* __restrict__ prof) {
+                    long long* __restrict__ prof, int dbg) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // 1 KB aligned base
   float* s_bias = reinterpret_cast<float*>(sm + Smem::bias);
@@ -166,8 +168,12 @@ mlp_chain_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ bl
           for (int ks = 0; ks < ksteps; ks += 2) {
             const uint32_t bytes = (ksteps - ks >= 2 ? 2u : 1u) * kbytes;
             mbar_wait(&bar_empty[pp.stage], pp.phase ^ 1);
-            mbar_arrive_expect_tx(&bar_full[pp.stage], bytes);
-            bulk_g2s(sm + Smem::ring + pp.stage * kStageBytes, src + (size_t)ks * kbytes, bytes, &bar_full[pp.stage]);
+            if (dbg & 1) {
+              mbar_arrive(&bar_full[pp.stage]);
+            } else {
+              mbar_arrive_expect_tx(&bar_full[pp.stage], bytes);
+              bulk_g2s(sm + Smem::ring + pp.stage * kStageBytes, src + (size_t)ks * kbytes, bytes, &bar_full[pp.stage]);
+            }
             pp.advance();
           }
         }
@@ -200,7 +206,7 @@ mlp_chain_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ bl
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               const int ks = ks0 + h;
-              if (ks < ksteps) {
+              if (ks < ksteps && !(dbg & 2)) {
                 const uint32_t wb = wb0 + h * 4 * slab_b;
                 const uint64_t b_hi = make_desc(wb, slab_b, 128);
                 const uint64_t b_lo = make_desc(wb + 2 * slab_b, slab_b, 128);
@@ -484,7 +490,7 @@ static int launch_chain(const Plan& p, const float* blob, const float* rays, int
   int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes), what);
   if (rc) return rc;
   kern<<<grid, kThreadsTc, bytes, s>>>(p, blob, rays, ray_stride, z, P, n_samples, tiles, raw, stash, gstash,
-                                       kMode == 0 ? g_tc_prof : nullptr);
+                                       kMode == 0 ? g_tc_prof : nullptr, g_tc_flags);
   count_launch();
   return check_cuda(cudaGetLastError(), what);
 }

@@ -1,0 +1,29 @@
+import os, sys, ctypes
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+from nerf_pytorch_b200 import ops, _lib
+lib = _lib.load()
+def timeit(fn, n=10, warm=3):
+    for _ in range(warm): fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n): fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+N, S = 4096, 192
+arch = ops.ArchSpec(n_freq_xyz=10, n_freq_dir=4, num_layers=4, hidden=128, skip_every=4)
+blob = ops.pack_weights(arch, torch.randn(arch.flat_param_count(), device="cuda") * 0.05)
+d = torch.randn(N, 3, device="cuda"); d[:, 2] = -1
+o = torch.tensor([[0.0, -2.0, 3.4]], device="cuda").expand(N, 3)
+rays = torch.cat([o, d, torch.full((N, 1), 2.0, device="cuda"), torch.full((N, 1), 6.0, device="cuda"), d / d.norm(dim=-1, keepdim=True)], -1).contiguous()
+z = torch.sort(torch.rand(N, S, device="cuda") * 4 + 2, -1).values.contiguous()
+prof = torch.zeros(148 * 4, dtype=torch.int64, device="cuda")
+lib.nerfb200_debug_tc_profile(ctypes.c_void_p(prof.data_ptr()))
+for flags, name in ((0, "normal"), (1, "no weight copies"), (2, "no MMAs"), (3, "neither")):
+    lib.nerfb200_debug_tc_flags(flags)
+    t = timeit(lambda: ops.mlp_fwd(arch, blob, rays, z, impl=1))
+    pr = prof.view(148, 4).double().mean(0) / 41.5
+    print(f"A0 fwd S=192 [{name}]: {t:.3f} ms   per tile: prologue {pr[0]:.0f} wait-mma {pr[1]:.0f} epilogue {pr[2]:.0f} total {pr[3]:.0f}")
+lib.nerfb200_debug_tc_flags(0)

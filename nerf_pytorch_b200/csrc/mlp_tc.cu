@@ -70,7 +70,7 @@ __device__ __forceinline__ void store_tile_coalesced(float* tbuf, const float (&
   for (int i = 0; i < 8; ++i) {
     const int r = 4 * i + (lane >> 3);
     const float4 v = *reinterpret_cast<const float4*>(tbuf + r * 32 + ((q ^ (r & 7)) << 2));
-    if (r < rows_valid) *reinterpret_cast<float4*>(gdst + (size_t)r * ld + 4 * q) = v;
+    if (r < rows_valid) __stcs(reinterpret_cast<float4*>(gdst + (size_t)r * ld + 4 * q), v);
   }
   __syncwarp();
 }
@@ -155,6 +155,7 @@ mlp_chain_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ bl
     // ===================== weight producer =====================
     if (lane == 0) {
       Pipe pp;
+      const uint64_t pol = l2_policy_evict_last();
       for (int64_t it = 0; it < my_tiles; ++it) {
         for (int step = 0; step < p.n_gemm; ++step) {
           // forward: layer `step`;  dgrad: layers in reverse, operand of the CONSUMER of layer t
@@ -172,7 +173,8 @@ mlp_chain_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ bl
               mbar_arrive(&bar_full[pp.stage]);
             } else {
               mbar_arrive_expect_tx(&bar_full[pp.stage], bytes);
-              bulk_g2s(sm + Smem::ring + pp.stage * kStageBytes, src + (size_t)ks * kbytes, bytes, &bar_full[pp.stage]);
+              bulk_g2s_hint(sm + Smem::ring + pp.stage * kStageBytes, src + (size_t)ks * kbytes, bytes,
+                            &bar_full[pp.stage], pol);
             }
             pp.advance();
           }

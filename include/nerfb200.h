@@ -65,8 +65,9 @@ int32_t nerfb200_version(void);
 const char* nerfb200_last_error(void);
 /* number of CUDA kernels this library has launched in this process (all threads) */
 int64_t nerfb200_launch_count(void);
-/* debug hook: device buffer of 4 int64 per CTA receiving the tcgen05 kernel's cycle counters
- * [prologue, wait-for-MMA, epilogue, total] of its epilogue thread 0; NULL switches it off. */
+/* debug hook: device buffer of 8 int64 per CTA receiving the tcgen05 forward kernel's cycle counters
+ * [prologue, wait-for-MMA, epilogue, total, tmem-load, chunk math+stores, tmem-store wait, head] of its
+ * epilogue thread 0; NULL switches it off. */
 void nerfb200_debug_tc_profile(void* buf);
 /* debug hook for timing experiments (results are garbage): bit 0 skips the weight copies, bit 1 the MMAs */
 void nerfb200_debug_tc_flags(int32_t flags);

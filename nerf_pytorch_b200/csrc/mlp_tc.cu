@@ -94,6 +94,95 @@ __device__ __forceinline__ int consumer_of(const Plan& p, int t) {
   return s;
 }
 
+
+// One 32-column chunk of one row in the epilogue (the hot loop of the chain kernels), specialised at compile time
+// on the two things that change its instruction mix: a narrow head reading this layer (kHead) and training
+// outputs (kTrain: ReLU bit mask + coalesced stash store).
+//   forward: y = max(acc + bias, lb)                      (lb = 0 with ReLU, -inf without; bias already holds the
+//                                                           per-ray direction term for layers_dir[0])
+//   dgrad  : y = (acc + sum_c d_raw[c] * W_head[c]) masked by the forward ReLU bit
+// then y -> tf32 hi / lo -> tensor memory (next layer's A operand).
+struct ChunkArgs {
+  const float* bias;      // fwd: 128 floats for this layer (per-thread pointer)
+  float lb;               // fwd: ReLU lower bound
+  const float* hw;        // head weights [hn][hk] in smem
+  int hk, hn, hcol;
+  float dr[4];            // dgrad: d_raw of this row
+  uint32_t mword_in;      // dgrad: ReLU mask word of this chunk
+  uint32_t* mword_out;    // fwd train: where to store the mask word (or nullptr when the row is out of range)
+  float* out_rows;        // train: stash / gstash rows of this warp (already offset to column c0)
+  int ld, lane, rows_valid;
+  float* tbuf;
+  uint32_t tmem_hi, tmem_lo;  // destination addresses (already offset to column c0)
+  bool has_next;
+};
+
+template <int kMode, bool kHead, bool kTrain>
+__device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int c0, const ChunkArgs& a, float (&hacc)[4]) {
+  float x[32];
+  uint32_t bits = 0;
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    float y[4] = {__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                  __uint_as_float(v[j + 3])};
+    if (kMode == 0) {
+      const float4 b = *reinterpret_cast<const float4*>(a.bias + c0 + j);
+      y[0] = fmaxf(y[0] + b.x, a.lb); y[1] = fmaxf(y[1] + b.y, a.lb);
+      y[2] = fmaxf(y[2] + b.z, a.lb); y[3] = fmaxf(y[3] + b.w, a.lb);
+      if (kHead) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (c < a.hn) {
+            const float4 w = *reinterpret_cast<const float4*>(a.hw + c * a.hk + c0 + j);
+            hacc[c] = fmaf(y[0], w.x, fmaf(y[1], w.y, fmaf(y[2], w.z, fmaf(y[3], w.w, hacc[c]))));
+          }
+      }
+      if (kTrain) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) bits |= (y[q] > 0.f ? 1u : 0u) << (j + q);
+      }
+    } else {
+      if (kHead) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (c < a.hn) {
+            const float4 w = *reinterpret_cast<const float4*>(a.hw + c * a.hk + c0 + j);
+            const float d = a.dr[(a.hcol + c) & 3];
+            y[0] = fmaf(d, w.x, y[0]); y[1] = fmaf(d, w.y, y[1]); y[2] = fmaf(d, w.z, y[2]); y[3] = fmaf(d, w.w, y[3]);
+          }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) y[q] = ((a.mword_in >> (j + q)) & 1u) ? y[q] : 0.f;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) x[j + q] = y[q];
+  }
+  if (kMode == 0 && kTrain && a.mword_out) *a.mword_out = bits;
+  if (kTrain && a.out_rows) store_tile_coalesced(a.tbuf, x, a.out_rows, a.ld, a.lane, a.rows_valid);
+  if (a.has_next) {
+    uint32_t hi[32], lo[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      hi[j] = tf32_hi(x[j]);
+      lo[j] = __float_as_uint(x[j] - __uint_as_float(hi[j]));
+    }
+    tmem_st32(a.tmem_hi, hi);
+    tmem_st32(a.tmem_lo, lo);
+  }
+}
+
+template <int kMode>
+__device__ __forceinline__ void epilogue_chunk_dispatch(bool head, bool train, const uint32_t (&v)[32], int c0,
+                                                        const ChunkArgs& a, float (&hacc)[4]) {
+  if (head) {
+    if (train) epilogue_chunk<kMode, true, true>(v, c0, a, hacc);
+    else epilogue_chunk<kMode, true, false>(v, c0, a, hacc);
+  } else {
+    if (train) epilogue_chunk<kMode, false, true>(v, c0, a, hacc);
+    else epilogue_chunk<kMode, false, false>(v, c0, a, hacc);
+  }
+}
+
 // kMode 0: forward, 1: dgrad
 template <int kMode>
 __global__ void __launch_bounds__(kThreadsTc, 1)
@@ -144,6 +233,7 @@ mlp_chain_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ bl
   float* s_headb = s_headw + ((hw1 + hw2 + 3) & ~3);
   if (tid < 4) s_headb[tid] = blob[p.h[0].b_off + tid];
   if (tid >= 4 && tid < 8) s_headb[tid] = p.n_head > 1 ? blob[p.h[1].b_off + tid - 4] : 0.f;
+  for (int i = tid; i < kMaxRaysPerTile * 32; i += kThreadsTc) s_encd[i] = 0.f;  // padding channels stay zero
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -182,8 +272,8 @@ mlp_chain_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ bl
       }
     }
   } else if (warp == 8) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
+    {
       Pipe pp;
       uint32_t a_phase = 0;
       const uint32_t e_hi = smem_u32(sm + Smem::e_hi), e_lo = smem_u32(sm + Smem::e_lo);
@@ -205,6 +295,7 @@ mlp_chain_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ bl
             mbar_wait(&bar_full[pp.stage], pp.phase);
             tc_fence_after();
             const uint32_t wb0 = smem_u32(sm + Smem::ring + pp.stage * kStageBytes);
+            if (elect_one()) {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               const int ks = ks0 + h;
@@ -229,9 +320,12 @@ mlp_chain_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ bl
               }
             }
             mma_commit(&bar_empty[pp.stage]);  // frees the ring stage once these MMAs have read it
+            }
+            __syncwarp();
             pp.advance();
           }
-          mma_commit(bar_acc);  // accumulator of this layer complete
+          if (elect_one()) mma_commit(bar_acc);  // accumulator of this layer complete
+          __syncwarp();
         }
       }
     }
@@ -243,7 +337,7 @@ mlp_chain_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ bl
     uint32_t acc_phase = 0;
     uint8_t* e_hi = sm + Smem::e_hi;
     uint8_t* e_lo = sm + Smem::e_lo;
-    long long t_pro = 0, t_wait = 0, t_epi = 0, t_all = clock64();
+    long long t_pro = 0, t_wait = 0, t_epi = 0, t_all = clock64(), t_ld = 0, t_ch = 0, t_st = 0, t_hd = 0;
     for (int64_t it = 0; it < my_tiles; ++it) {
       long long t0 = clock64();
       const int64_t tile = blockIdx.x + it * gridDim.x;
@@ -266,7 +360,10 @@ mlp_chain_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ bl
         {
           const float* rr = rays + ray * ray_stride;
           const float zz = z[pt];
-          float* sx = (stash && valid) ? stash + (size_t)P * p.enc_cum[0] + (size_t)pt * p.dim_xyz_pad : nullptr;
+          // the encoding also goes to the stash for the backward: through the coalesced path below when the
+          // padded width is the usual 64, else element by element
+          float* sx = (stash && valid && p.dim_xyz_pad != 64)
+                          ? stash + (size_t)P * p.enc_cum[0] + (size_t)pt * p.dim_xyz_pad : nullptr;
           const int nf = p.n_freq_xyz, mid = nf >> 1;
           const int f0 = half ? mid : 0, f1 = half ? nf : mid;
           const int base = p.inc_xyz ? 3 : 0;
@@ -305,14 +402,30 @@ mlp_chain_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ bl
             const int j = i / gd.n, n = i - j * gd.n;
             float a = 0.f;
             for (int k = 0; k < p.dim_dir; ++k) a = fmaf(s_encd[j * 32 + k], wv[k * gd.n + n], a);
-            s_viewb[j * 64 + n] = a;
+            s_viewb[j * 64 + n] = a + s_bias[(p.n_gemm - 1) * 128 + n];  // per-ray bias of layers_dir[0]
           }
         }
         fence_proxy_async();  // E_hi / E_lo were written through the generic proxy; the MMAs read them via the async proxy
         epi_bar256();         // also publishes s_viewb
-        if (stash && valid && p.use_viewdirs && half == 0) {
-          float* sd = stash + (size_t)P * p.enc_cum[1] + (size_t)pt * p.dim_dir_pad;
-          for (int k = 0; k < p.dim_dir_pad; ++k) sd[k] = k < p.dim_dir ? s_encd[ray_slot * 32 + k] : 0.f;
+        if (stash) {
+          if (p.dim_xyz_pad == 64) {
+            // this thread's row, channels [32*half, 32*half + 32): hi + lo is the exact fp32 value
+            float x[32];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const int off = (8 * half + q) * kSlabBytes + row * 16;
+              const float4 h4 = *reinterpret_cast<const float4*>(e_hi + off);
+              const float4 l4 = *reinterpret_cast<const float4*>(e_lo + off);
+              x[4 * q] = h4.x + l4.x; x[4 * q + 1] = h4.y + l4.y; x[4 * q + 2] = h4.z + l4.z; x[4 * q + 3] = h4.w + l4.w;
+            }
+            store_tile_coalesced(tbuf, x, stash + (size_t)P * p.enc_cum[0] + (size_t)wrow0 * 64 + 32 * half, 64, lane,
+                                 rows_valid);
+          }
+          if (valid && p.use_viewdirs && half == 0) {
+            float4* sd = reinterpret_cast<float4*>(stash + (size_t)P * p.enc_cum[1] + (size_t)pt * p.dim_dir_pad);
+            const float4* se = reinterpret_cast<const float4*>(s_encd + ray_slot * 32);
+            for (int k = 0; k < (p.dim_dir_pad >> 2); ++k) __stcs(sd + k, se[k]);
+          }
         }
         mbar_arrive(bar_a);
       } else {
@@ -355,77 +468,38 @@ mlp_chain_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ bl
         const long long t1 = clock64();
         t_wait += t1 - t0;
 
-        uint32_t v0[32], v1[32];
-        if (has_mma) {
-          tmem_ld32(tmem + lane_base + kColAcc + cbase, v0);
-          if (ncol == 64) tmem_ld32(tmem + lane_base + kColAcc + cbase + 32, v1);
-          tmem_wait_ld();
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v0[j] = v1[j] = 0u;
-        }
+        const long long t2 = clock64();
+        t_ld += t2 - t1;
 
-        auto chunk = [&](uint32_t (&v)[32], int c0) {  // c0: first column of this 32-column chunk
-          float x[32];
-          uint32_t bits = 0;
-          uint32_t mword = 0xFFFFFFFFu;
-          if (kMode == 1 && g.relu) mword = valid ? mask_row[c0 >> 5] : 0u;
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float y[4] = {__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                          __uint_as_float(v[j + 3])};
-            if (kMode == 0) {
-              const float4 b = *reinterpret_cast<const float4*>(s_bias + t * 128 + c0 + j);
-              y[0] += b.x; y[1] += b.y; y[2] += b.z; y[3] += b.w;
-              if (is_dir) {
-                const float4 vb = *reinterpret_cast<const float4*>(s_viewb + ray_slot * 64 + c0 + j);
-                y[0] += vb.x; y[1] += vb.y; y[2] += vb.z; y[3] += vb.w;
-              }
-              if (g.relu) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) y[q] = fmaxf(y[q], 0.f);
-              }
-              if (hsel >= 0) {
-#pragma unroll
-                for (int c = 0; c < 4; ++c)
-                  if (c < hn) {
-                    const float4 w = *reinterpret_cast<const float4*>(hw + c * hk + c0 + j);
-                    hacc[c] = fmaf(y[0], w.x, fmaf(y[1], w.y, fmaf(y[2], w.z, fmaf(y[3], w.w, hacc[c]))));
-                  }
-              }
-#pragma unroll
-              for (int q = 0; q < 4; ++q) bits |= (y[q] > 0.f ? 1u : 0u) << (j + q);
+        {
+          ChunkArgs ca;
+          const bool train = kMode == 0 ? (stash != nullptr) : true;
+          ca.bias = (kMode == 0) ? (is_dir ? s_viewb + ray_slot * 64 : s_bias + t * 128) : nullptr;
+          ca.lb = g.relu ? 0.f : -3.4e38f;
+          ca.hw = hw; ca.hk = hk; ca.hn = hn; ca.hcol = hcol;
+          ca.dr[0] = dr[0]; ca.dr[1] = dr[1]; ca.dr[2] = dr[2]; ca.dr[3] = dr[3];
+          ca.ld = g.n; ca.lane = lane; ca.rows_valid = rows_valid; ca.tbuf = tbuf; ca.has_next = has_next;
+          for (int ch = 0; ch < (ncol >> 5); ++ch) {
+            const int c0 = cbase + 32 * ch;
+            ca.mword_in = 0xFFFFFFFFu;
+            if (kMode == 1 && g.relu) ca.mword_in = valid ? mask_row[c0 >> 5] : 0u;
+            ca.mword_out = (kMode == 0 && mask_row && valid) ? mask_row + (c0 >> 5) : nullptr;
+            ca.out_rows = out_rows ? out_rows + c0 : nullptr;
+            ca.tmem_hi = tmem + lane_base + kColAhi + c0;
+            ca.tmem_lo = tmem + lane_base + kColAlo + c0;
+            uint32_t v[32];
+            if (has_mma) {
+              tmem_ld32(tmem + lane_base + kColAcc + c0, v);
+              tmem_wait_ld();
             } else {
-              if (hsel >= 0) {
 #pragma unroll
-                for (int c = 0; c < 4; ++c)
-                  if (c < hn) {
-                    const float4 w = *reinterpret_cast<const float4*>(hw + c * hk + c0 + j);
-                    const float d = dr[(hcol + c) & 3];
-                    y[0] = fmaf(d, w.x, y[0]); y[1] = fmaf(d, w.y, y[1]); y[2] = fmaf(d, w.z, y[2]); y[3] = fmaf(d, w.w, y[3]);
-                  }
-              }
-#pragma unroll
-              for (int q = 0; q < 4; ++q) y[q] = ((mword >> (j + q)) & 1u) ? y[q] : 0.f;
+              for (int j = 0; j < 32; ++j) v[j] = 0u;
             }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) x[j + q] = y[q];
+            epilogue_chunk_dispatch<kMode>(hsel >= 0, train, v, c0, ca, hacc);
           }
-          if (kMode == 0 && mask_row && valid) mask_row[c0 >> 5] = bits;
-          if (out_rows) store_tile_coalesced(tbuf, x, out_rows + c0, g.n, lane, rows_valid);
-          if (has_next) {
-            uint32_t hi[32], lo[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              hi[j] = tf32_hi(x[j]);
-              lo[j] = __float_as_uint(x[j] - __uint_as_float(hi[j]));
-            }
-            tmem_st32(tmem + lane_base + kColAhi + c0, hi);
-            tmem_st32(tmem + lane_base + kColAlo + c0, lo);
-          }
-        };
-        chunk(v0, cbase);
-        if (ncol == 64) chunk(v1, cbase + 32);
+        }
+        const long long t3 = clock64();
+        t_ch += t3 - t2;
 
         if (kMode == 0 && hsel >= 0 && half == 1)
           *reinterpret_cast<float4*>(s_hpart + (hsel * 128 + row) * 4) = make_float4(hacc[0], hacc[1], hacc[2], hacc[3]);
@@ -436,6 +510,8 @@ mlp_chain_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ bl
         } else {
           tc_fence_before();
         }
+        const long long t4 = clock64();
+        t_st += t4 - t3;
         if (kMode == 0 && hsel >= 0) {
           epi_bar256();  // the other half's partial dot products are in s_hpart
           if (half == 0 && valid) {
@@ -448,13 +524,18 @@ mlp_chain_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ bl
           }
         }
         t_epi += clock64() - t1;
+        t_hd += clock64() - t4;
       }
     }
     if (prof && tid == 0) {
-      prof[blockIdx.x * 4 + 0] = t_pro;
-      prof[blockIdx.x * 4 + 1] = t_wait;
-      prof[blockIdx.x * 4 + 2] = t_epi;
-      prof[blockIdx.x * 4 + 3] = clock64() - t_all;
+      prof[blockIdx.x * 8 + 0] = t_pro;
+      prof[blockIdx.x * 8 + 1] = t_wait;
+      prof[blockIdx.x * 8 + 2] = t_epi;
+      prof[blockIdx.x * 8 + 3] = clock64() - t_all;
+      prof[blockIdx.x * 8 + 4] = t_ld;
+      prof[blockIdx.x * 8 + 5] = t_ch;
+      prof[blockIdx.x * 8 + 6] = t_st;
+      prof[blockIdx.x * 8 + 7] = t_hd;
     }
   }
 

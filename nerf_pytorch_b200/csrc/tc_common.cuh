@@ -82,6 +82,17 @@ __device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a_tmem, uint64_t b, 
       "r"(a_tmem), "l"(b), "r"(idesc), "r"(acc)
       : "memory");
 }
+// one lane of a converged warp (the warp runs the surrounding loop uniformly so that descriptors and addresses
+// live in uniform registers; only the tcgen05 instruction itself is predicated on the elected lane)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n.reg .b32 rx;\n.reg .pred px;\n"
+      "elect.sync rx|px, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, px;\n}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");

@@ -58,13 +58,13 @@ for archname, kw in (("A0", dict(num_layers=4, hidden=128, skip_every=4)), ("A1"
 # cycle breakdown of the tcgen05 kernel (epilogue thread 0 of every CTA)
 import ctypes
 from nerf_pytorch_b200 import _lib
-prof = torch.zeros(148 * 4, dtype=torch.int64, device="cuda")
+prof = torch.zeros(148 * 8, dtype=torch.int64, device="cuda")
 _lib.load().nerfb200_debug_tc_profile(ctypes.c_void_p(prof.data_ptr()))
 arch = ops.ArchSpec(n_freq_xyz=10, n_freq_dir=4, num_layers=4, hidden=128, skip_every=4)
 blob = ops.pack_weights(arch, torch.randn(arch.flat_param_count(), device="cuda") * 0.05)
 z = torch.sort(torch.rand(N, 192, device="cuda") * 4 + 2, -1).values.contiguous()
 ops.mlp_fwd(arch, blob, rays, z, impl=1); torch.cuda.synchronize()
-pr = prof.view(148, 4).double()
+pr = prof.view(148, 8).double()[:, :4]
 print("A0 S=192 per-CTA cycles: prologue %.0f  wait-mma %.0f  epilogue %.0f  total %.0f (tiles/CTA %.1f)" % (*pr.mean(0).tolist(), 4096*192/128/148))
 _lib.load().nerfb200_debug_tc_profile(None)
 

@@ -19,11 +19,11 @@ d = torch.randn(N, 3, device="cuda"); d[:, 2] = -1
 o = torch.tensor([[0.0, -2.0, 3.4]], device="cuda").expand(N, 3)
 rays = torch.cat([o, d, torch.full((N, 1), 2.0, device="cuda"), torch.full((N, 1), 6.0, device="cuda"), d / d.norm(dim=-1, keepdim=True)], -1).contiguous()
 z = torch.sort(torch.rand(N, S, device="cuda") * 4 + 2, -1).values.contiguous()
-prof = torch.zeros(148 * 4, dtype=torch.int64, device="cuda")
+prof = torch.zeros(148 * 8, dtype=torch.int64, device="cuda")
 lib.nerfb200_debug_tc_profile(ctypes.c_void_p(prof.data_ptr()))
-for flags, name in ((0, "normal"), (1, "no weight copies"), (2, "no MMAs"), (3, "neither")):
+for flags, name, st in ((0, "normal", False), (2, "no MMAs", False), (0, "normal+stash", True), (2, "no MMAs+stash", True)):
     lib.nerfb200_debug_tc_flags(flags)
-    t = timeit(lambda: ops.mlp_fwd(arch, blob, rays, z, impl=1))
-    pr = prof.view(148, 4).double().mean(0) / 41.5
-    print(f"A0 fwd S=192 [{name}]: {t:.3f} ms   per tile: prologue {pr[0]:.0f} wait-mma {pr[1]:.0f} epilogue {pr[2]:.0f} total {pr[3]:.0f}")
+    t = timeit(lambda: ops.mlp_fwd(arch, blob, rays, z, impl=1, want_stash=st))
+    pr = prof.view(148, 8).double().mean(0) / 41.5
+    print(f"A0 fwd S=192 [{name}]: {t:.3f} ms  per tile: prologue {pr[0]:.0f} wait-mma {pr[1]:.0f} epilogue {pr[2]:.0f} total {pr[3]:.0f} | per layer: tmem-ld {pr[4]/6:.0f} chunks {pr[5]/6:.0f} st-wait {pr[6]/6:.0f} head/bar {pr[7]/6:.0f}")
 lib.nerfb200_debug_tc_flags(0)

@@ -15,7 +15,7 @@
 //              per-warp swizzled shared-memory transpose so that every global store is a full 128-byte row.
 //   warp 8     MMA issuer: one elected lane, tcgen05.mma.kind::tf32 M=128, N=128|64, K=8, three per k-step;
 //              A from tensor memory (hidden activations / gradients) or shared memory (encodings), B = pre-split
-//              weights from the shared-memory ring (two k-steps per stage).
+//              weights from the shared-memory ring (four k-steps per stage).
 //   warp 9     weight producer: one cp.async.bulk per stage from the L2-resident blob, mbarrier complete_tx.
 // Tensor memory (512 columns): [0,128) accumulator, [128,256) A_hi, [256,384) A_lo.
 // The direction encoding enters layers_dir[0] through a per-ray fp32 bias computed on the CUDA cores (it is
@@ -33,8 +33,9 @@ void set_tc_flags(int f) { g_tc_flags = f; }
 namespace tc {
 constexpr int kEpiThreads = 256;
 constexpr int kThreadsTc = 320;
-constexpr int kStages = 6;            // weight ring depth
-constexpr int kStageBytes = 16384;    // two k-steps of hi+lo weights for N = 128
+constexpr int kStages = 3;            // weight ring depth
+constexpr int kStepsPerStage = 4;     // k-steps (8 KB each for N = 128) per ring stage
+constexpr int kStageBytes = kStepsPerStage * 8192;
 constexpr int kSlabBytes = 2048;      // 128 rows x 16 B
 constexpr int kMaxRaysPerTile = 10;
 constexpr uint32_t kTmemCols = 512;
@@ -256,8 +257,8 @@ mlp_chain_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ bl
           const uint32_t kbytes = kMode == 0 ? 64u * g.n : 64u * g.k_h;  // one k-step (hi + lo)
           const uint8_t* src = reinterpret_cast<const uint8_t*>(blob + (kMode == 0 ? g.tc_off : g.tcd_off));
           const int ksteps = (kMode == 0 ? g.k_tc : g.n) >> 3;
-          for (int ks = 0; ks < ksteps; ks += 2) {
-            const uint32_t bytes = (ksteps - ks >= 2 ? 2u : 1u) * kbytes;
+          for (int ks = 0; ks < ksteps; ks += kStepsPerStage) {
+            const uint32_t bytes = (uint32_t)min(kStepsPerStage, ksteps - ks) * kbytes;
             mbar_wait(&bar_empty[pp.stage], pp.phase ^ 1);
             if (dbg & 1) {
               mbar_arrive(&bar_full[pp.stage]);
@@ -291,13 +292,13 @@ mlp_chain_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ bl
           mbar_wait(bar_a, a_phase);
           a_phase ^= 1;
           tc_fence_after();
-          for (int ks0 = 0; ks0 < ksteps; ks0 += 2) {
+          for (int ks0 = 0; ks0 < ksteps; ks0 += kStepsPerStage) {
             mbar_wait(&bar_full[pp.stage], pp.phase);
             tc_fence_after();
             const uint32_t wb0 = smem_u32(sm + Smem::ring + pp.stage * kStageBytes);
             if (elect_one()) {
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
+            for (int h = 0; h < kStepsPerStage; ++h) {
               const int ks = ks0 + h;
               if (ks < ksteps && !(dbg & 2)) {
                 const uint32_t wb = wb0 + h * 4 * slab_b;

@@ -111,6 +111,12 @@ int launch_mlp_fwd_tc(const Plan& p, const float* blob, const float* rays, int r
 // ---------------------------------------------------------------------------------------------
 #ifdef __CUDACC__
 
+// Stash row swizzle.  The activation / gradient stashes ([points][n] fp32, workspace private to this library) keep
+// every 16-byte chunk of a row at chunk index (q ^ (point & 7)) inside its 128-byte segment.  Global access
+// patterns are unchanged (a permutation inside each 128 B line), and a 128-row tile of the stash is byte-identical
+// to a bank-conflict-free shared-memory tile, so the tensor-core kernels write it with ONE cp.async.bulk per layer.
+__device__ __forceinline__ int swz_col(int col, int64_t point) { return (((col >> 2) ^ (int)(point & 7)) << 2) | (col & 3); }
+
 // Positional encoding of one scalar coordinate (nerf_helpers.py:113-157): writes x (if include) and
 // sin/cos(x * f_i) at the reference's channel positions for coordinate c of 3:
 //   [x y z | sin(f0 xyz) | cos(f0 xyz) | sin(f1 xyz) | ...]

@@ -255,7 +255,7 @@ mlp_fwd_simt_kernel(const __grid_constant__ Plan p, const FwdSmem sm, const floa
           }
           const int row = r * 16 + ty, col = tx * 4 + 64 * j;
           *reinterpret_cast<float4*>(act + row * sm.act_ld + col) = v;
-          if (st && p0 + row < P) *reinterpret_cast<float4*>(st + (size_t)(p0 + row) * g.n + col) = v;
+          if (st && p0 + row < P) *reinterpret_cast<float4*>(st + (size_t)(p0 + row) * g.n + swz_col(col, p0 + row)) = v;
         }
       }
       __syncthreads();
@@ -386,13 +386,13 @@ mlp_bwd_dgrad_kernel(const __grid_constant__ Plan p, const BwdSmem sm, const flo
           }
           const bool inb = p0 + row < P;
           if (gt.relu) {
-            float4 a = inb ? *reinterpret_cast<const float4*>(st + (size_t)(p0 + row) * gt.n + col)
+            float4 a = inb ? *reinterpret_cast<const float4*>(st + (size_t)(p0 + row) * gt.n + swz_col(col, p0 + row))
                            : make_float4(0.f, 0.f, 0.f, 0.f);
             v.x = a.x > 0.f ? v.x : 0.f; v.y = a.y > 0.f ? v.y : 0.f;
             v.z = a.z > 0.f ? v.z : 0.f; v.w = a.w > 0.f ? v.w : 0.f;
           }
           *reinterpret_cast<float4*>(G + row * sm.g_ld + col) = v;
-          if (inb) *reinterpret_cast<float4*>(gs + (size_t)(p0 + row) * gt.n + col) = v;
+          if (inb) *reinterpret_cast<float4*>(gs + (size_t)(p0 + row) * gt.n + swz_col(col, p0 + row)) = v;
         }
       }
       __syncthreads();
@@ -463,7 +463,7 @@ __device__ __forceinline__ void wgrad_block(const Plan& p, const WgItem& it, con
     for (int i = tid; i < kWgPts * vy; i += kThreads) {
       const int pp = i / vy, cc = i - pp * vy;
       float* dst = ys[buf] + pp * ldy + cc * 4;
-      if (q0 + pp < pt_end) cp_async16(dst, dY + (size_t)(q0 + pp) * g.n + cc * 4);
+      if (q0 + pp < pt_end) cp_async16(dst, dY + (size_t)(q0 + pp) * g.n + swz_col(cc * 4, q0 + pp));
       else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     if (it.kind == 0) {
@@ -471,7 +471,7 @@ __device__ __forceinline__ void wgrad_block(const Plan& p, const WgItem& it, con
       for (int i = tid; i < kWgPts * vx; i += kThreads) {
         const int pp = i / vx, cc = i - pp * vx;
         float* dst = xs[buf] + pp * ldx + cc * 4;
-        if (q0 + pp < pt_end) cp_async16(dst, X + (size_t)(q0 + pp) * xw + cc * 4);
+        if (q0 + pp < pt_end) cp_async16(dst, X + (size_t)(q0 + pp) * xw + swz_col(cc * 4, q0 + pp));
         else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
       }
     } else {
@@ -558,7 +558,7 @@ __device__ __forceinline__ void wgrad_head(const Plan& p, const WgItem& it, cons
   for (int64_t pt = pt_begin + grp; pt < pt_end; pt += groups) {
     const float4 d = reinterpret_cast<const float4*>(d_raw)[pt];
     const float dv[4] = {d.x, d.y, d.z, d.w};
-    const float x = X[(size_t)pt * xw + k];
+    const float x = X[(size_t)pt * xw + swz_col(k, pt)];
     for (int c = 0; c < h.n_out; ++c) {
       acc[c] = fmaf(dv[h.out_col + c], x, acc[c]);
       bacc[c] += dv[h.out_col + c];

@@ -33,20 +33,24 @@ void set_tc_flags(int f) { g_tc_flags = f; }
 namespace tc {
 constexpr int kEpiThreads = 256;
 constexpr int kThreadsTc = 320;
-constexpr int kStages = 3;            // weight ring depth
+constexpr int kMaxStages = 3;         // weight ring depth (2 while a forward also stages its stash tile)
 constexpr int kStepsPerStage = 4;     // k-steps (8 KB each for N = 128) per ring stage
 constexpr int kStageBytes = kStepsPerStage * 8192;
 constexpr int kSlabBytes = 2048;      // 128 rows x 16 B
 constexpr int kMaxRaysPerTile = 10;
 constexpr uint32_t kTmemCols = 512;
-constexpr uint32_t kColAcc = 0, kColAhi = 128, kColAlo = 256;
+constexpr uint32_t kColAcc = 0, kColAhi = 128, kColAlo = 256, kColElo = 384;  // E_lo: lo parts of the encodings (64 cols)
 
+// Shared memory map (bytes from the 1 KB-aligned base).  The hi parts of the encodings are an SS-mode A operand in
+// shared memory, their lo parts live in tensor memory (columns [384, 448)).  `stage` is the 64 KB stash staging tile:
+// a byte-exact image of one 128-row tile of a stash layer, written by the epilogue and shipped with one
+// cp.async.bulk; its first 32 KB double as the per-warp transpose tiles of the encoding stash.
 struct Smem {
   static constexpr int e_hi = 0;                               // 16 slabs (K <= 64) x 2 KB   (forward only)
-  static constexpr int e_lo = e_hi + 16 * kSlabBytes;
-  static constexpr int ring = e_lo + 16 * kSlabBytes;          // kStages x 16 KB
-  static constexpr int tbuf = ring + kStages * kStageBytes;    // 8 warps x 4 KB transpose tiles
-  static constexpr int bias = tbuf + 8 * 4096;                 // kMaxGemm x 128 floats
+  static constexpr int ring = e_hi + 16 * kSlabBytes;          // kMaxStages x 32 KB
+  static constexpr int stage = ring + kMaxStages * kStageBytes;  // 64 KB staging tile (training)
+  static constexpr int tbuf = stage;                           // 8 warps x 4 KB transpose tiles (encoding stash)
+  static constexpr int bias = stage + 65536;                   // kMaxGemm x 128 floats
   static constexpr int headw = bias + kMaxGemm * 128 * 4;      // 4*128 + 3*64 floats (+pad) and 8 bias floats
   static constexpr int viewb = headw + (4 * 128 + 3 * 64 + 16) * 4;   // kMaxRaysPerTile x 64
   static constexpr int encd = viewb + kMaxRaysPerTile * 64 * 4;       // kMaxRaysPerTile x 32
@@ -78,8 +82,8 @@ __device__ __forceinline__ void store_tile_coalesced(float* tbuf, const float (&
 
 struct Pipe {  // role-local ring state
   uint32_t stage = 0, phase = 0;
-  __device__ __forceinline__ void advance() {
-    if (++stage == kStages) { stage = 0; phase ^= 1; }
+  __device__ __forceinline__ void advance(uint32_t n_stages) {
+    if (++stage == n_stages) { stage = 0; phase ^= 1; }
   }
 };
 
@@ -111,9 +115,8 @@ struct ChunkArgs {
   float dr[4];            // dgrad: d_raw of this row
   uint32_t mword_in;      // dgrad: ReLU mask word of this chunk
   uint32_t* mword_out;    // fwd train: where to store the mask word (or nullptr when the row is out of range)
-  float* out_rows;        // train: stash / gstash rows of this warp (already offset to column c0)
-  int ld, lane, rows_valid;
-  float* tbuf;
+  uint8_t* stg_row;       // train: this row inside the staging tile (row * n * 4 bytes in), or nullptr
+  int row7;               // row & 7: the stash chunk swizzle of this row (common.cuh swz_col)
   uint32_t tmem_hi, tmem_lo;  // destination addresses (already offset to column c0)
   bool has_next;
 };
@@ -159,7 +162,12 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int c0, 
     for (int q = 0; q < 4; ++q) x[j + q] = y[q];
   }
   if (kMode == 0 && kTrain && a.mword_out) *a.mword_out = bits;
-  if (kTrain && a.out_rows) store_tile_coalesced(a.tbuf, x, a.out_rows, a.ld, a.lane, a.rows_valid);
+  if (kTrain && a.stg_row) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      *reinterpret_cast<float4*>(a.stg_row + ((((c0 >> 2) + q) ^ a.row7) << 4)) =
+          make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+  }
   if (a.has_next) {
     uint32_t hi[32], lo[32];
 #pragma unroll
@@ -201,16 +209,19 @@ mlp_chain_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ bl
   float* s_encd = reinterpret_cast<float*>(sm + Smem::encd);
   float* s_hpart = reinterpret_cast<float*>(sm + Smem::hpart);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + Smem::bars);
-  uint64_t* bar_full = bars;                   // [kStages]  weights landed
-  uint64_t* bar_empty = bars + kStages;        // [kStages]  stage consumed by the MMAs
-  uint64_t* bar_a = bars + 2 * kStages;        // A operand of the next layer is ready (256 arrivals)
-  uint64_t* bar_acc = bars + 2 * kStages + 1;  // accumulator of the current layer is complete
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 2);
+  uint64_t* bar_full = bars;                      // [kMaxStages]  weights landed
+  uint64_t* bar_empty = bars + kMaxStages;        // [kMaxStages]  stage consumed by the MMAs
+  uint64_t* bar_a = bars + 2 * kMaxStages;        // A operand of the next layer is ready (256 arrivals)
+  uint64_t* bar_acc = bars + 2 * kMaxStages + 1;  // accumulator of the current layer is complete
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 2);
+  const bool training = kMode == 1 || stash != nullptr;
+  const uint32_t n_stages = kMaxStages;
+  uint8_t* staging = sm + Smem::stage;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
-    for (int i = 0; i < kStages; ++i) {
+    for (int i = 0; i < kMaxStages; ++i) {
       mbar_init(&bar_full[i], 1);
       mbar_init(&bar_empty[i], 1);
     }
@@ -267,7 +278,7 @@ mlp_chain_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ bl
               bulk_g2s_hint(sm + Smem::ring + pp.stage * kStageBytes, src + (size_t)ks * kbytes, bytes,
                             &bar_full[pp.stage], pol);
             }
-            pp.advance();
+            pp.advance(n_stages);
           }
         }
       }
@@ -277,7 +288,7 @@ mlp_chain_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ bl
     {
       Pipe pp;
       uint32_t a_phase = 0;
-      const uint32_t e_hi = smem_u32(sm + Smem::e_hi), e_lo = smem_u32(sm + Smem::e_lo);
+      const uint32_t e_hi = smem_u32(sm + Smem::e_hi);
       for (int64_t it = 0; it < my_tiles; ++it) {
         for (int step = 0; step < p.n_gemm; ++step) {
           const int t = kMode == 0 ? step : p.n_gemm - 1 - step;
@@ -313,9 +324,9 @@ mlp_chain_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ bl
                 } else {
                   const uint32_t off = (uint32_t)(ks - ksteps_h) * 2 * kSlabBytes;
                   const uint64_t a_hi = make_desc(e_hi + off, kSlabBytes, 128);
-                  const uint64_t a_lo = make_desc(e_lo + off, kSlabBytes, 128);
+                  const uint32_t a_lo = tmem + kColElo + 8 * (ks - ksteps_h);
                   mma_ss(tmem + kColAcc, a_hi, b_hi, idesc, acc0);
-                  mma_ss(tmem + kColAcc, a_lo, b_hi, idesc, 1u);
+                  mma_ts(tmem + kColAcc, a_lo, b_hi, idesc, 1u);
                   mma_ss(tmem + kColAcc, a_hi, b_lo, idesc, 1u);
                 }
               }
@@ -323,7 +334,7 @@ mlp_chain_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ bl
             mma_commit(&bar_empty[pp.stage]);  // frees the ring stage once these MMAs have read it
             }
             __syncwarp();
-            pp.advance();
+            pp.advance(n_stages);
           }
           if (elect_one()) mma_commit(bar_acc);  // accumulator of this layer complete
           __syncwarp();
@@ -337,7 +348,6 @@ mlp_chain_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ bl
     float* tbuf = reinterpret_cast<float*>(sm + Smem::tbuf) + warp * 1024;
     uint32_t acc_phase = 0;
     uint8_t* e_hi = sm + Smem::e_hi;
-    uint8_t* e_lo = sm + Smem::e_lo;
     long long t_pro = 0, t_wait = 0, t_epi = 0, t_all = clock64(), t_ld = 0, t_ch = 0, t_st = 0, t_hd = 0;
     for (int64_t it = 0; it < my_tiles; ++it) {
       long long t0 = clock64();
@@ -374,7 +384,9 @@ mlp_chain_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ bl
             const float lo = v - __uint_as_float(hi);
             const int off = (k >> 2) * kSlabBytes + row * 16 + (k & 3) * 4;
             *reinterpret_cast<uint32_t*>(e_hi + off) = hi;
-            *reinterpret_cast<float*>(e_lo + off) = lo;
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(tmem + lane_base + kColElo + k),
+                         "r"(__float_as_uint(lo))
+                         : "memory");
           };
           for (int c = 0; c < 3; ++c) {
             const float x = __fadd_rn(rr[c], __fmul_rn(rr[3 + c], zz));  // pts = ro + rd * z (train_utils.py:67)
@@ -406,18 +418,25 @@ mlp_chain_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ bl
             s_viewb[j * 64 + n] = a + s_bias[(p.n_gemm - 1) * 128 + n];  // per-ray bias of layers_dir[0]
           }
         }
-        fence_proxy_async();  // E_hi / E_lo were written through the generic proxy; the MMAs read them via the async proxy
+        tmem_wait_st();       // E_lo went to tensor memory
+        tc_fence_before();
+        fence_proxy_async();  // E_hi was written through the generic proxy; the MMAs read it via the async proxy
+        if (training && tid == 0) bulk_wait_read();  // transpose tiles below overlap the staging tile
         epi_bar256();         // also publishes s_viewb
         if (stash) {
           if (p.dim_xyz_pad == 64) {
-            // this thread's row, channels [32*half, 32*half + 32): hi + lo is the exact fp32 value
+            // this thread's row, channels [32*half, 32*half + 32): hi (smem) + lo (tensor memory) is the exact fp32 value
             float x[32];
+            uint32_t lo32[32];
+            tmem_ld32(tmem + lane_base + kColElo + 32 * half, lo32);
+            tmem_wait_ld();
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-              const int off = (8 * half + q) * kSlabBytes + row * 16;
-              const float4 h4 = *reinterpret_cast<const float4*>(e_hi + off);
-              const float4 l4 = *reinterpret_cast<const float4*>(e_lo + off);
-              x[4 * q] = h4.x + l4.x; x[4 * q + 1] = h4.y + l4.y; x[4 * q + 2] = h4.z + l4.z; x[4 * q + 3] = h4.w + l4.w;
+              const float4 h4 = *reinterpret_cast<const float4*>(e_hi + (8 * half + q) * kSlabBytes + row * 16);
+              x[4 * q] = h4.x + __uint_as_float(lo32[4 * q]);
+              x[4 * q + 1] = h4.y + __uint_as_float(lo32[4 * q + 1]);
+              x[4 * q + 2] = h4.z + __uint_as_float(lo32[4 * q + 2]);
+              x[4 * q + 3] = h4.w + __uint_as_float(lo32[4 * q + 3]);
             }
             store_tile_coalesced(tbuf, x, stash + (size_t)P * p.enc_cum[0] + (size_t)wrow0 * 64 + 32 * half, 64, lane,
                                  rows_valid);
@@ -453,13 +472,16 @@ mlp_chain_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ bl
         const int ncol = g.n >> 1;          // columns of this thread's half
         const int cbase = half * ncol;
         // training side outputs / inputs of this layer
-        float* out_rows = nullptr;          // fwd: activation stash; dgrad: gradient stash  (this warp's 32-row block)
-        if (kMode == 0 ? (stash != nullptr) : true)
-          out_rows = (kMode == 0 ? stash : gstash) + (size_t)P * g.cum_n + (size_t)wrow0 * g.n;
         uint32_t* mask_row = nullptr;
         if (kMode == 0 ? (stash != nullptr) : (g.relu != 0))
           mask_row = reinterpret_cast<uint32_t*>(stash) + (size_t)P * (p.mask_base + g.mask_cum) + (size_t)pt * (g.n >> 5);
 
+        // dgrad: fetch this row's ReLU mask words now so that their latency hides behind the MMA wait
+        uint32_t mw[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};
+        if (kMode == 1 && g.relu) {
+          mw[0] = valid ? __ldg(mask_row + (cbase >> 5)) : 0u;
+          mw[1] = (valid && ncol == 64) ? __ldg(mask_row + (cbase >> 5) + 1) : 0u;
+        }
         t0 = clock64();
         if (has_mma) {
           mbar_wait(bar_acc, acc_phase);
@@ -468,6 +490,10 @@ mlp_chain_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ bl
         }
         const long long t1 = clock64();
         t_wait += t1 - t0;
+        if (training) {  // the previous layer's bulk store must have finished reading the staging tile
+          if (tid == 0) bulk_wait_read();
+          epi_bar256();
+        }
 
         const long long t2 = clock64();
         t_ld += t2 - t1;
@@ -479,13 +505,13 @@ mlp_chain_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ bl
           ca.lb = g.relu ? 0.f : -3.4e38f;
           ca.hw = hw; ca.hk = hk; ca.hn = hn; ca.hcol = hcol;
           ca.dr[0] = dr[0]; ca.dr[1] = dr[1]; ca.dr[2] = dr[2]; ca.dr[3] = dr[3];
-          ca.ld = g.n; ca.lane = lane; ca.rows_valid = rows_valid; ca.tbuf = tbuf; ca.has_next = has_next;
+          ca.has_next = has_next;
+          ca.row7 = row & 7;
+          ca.stg_row = train ? staging + (size_t)row * g.n * 4 : nullptr;
           for (int ch = 0; ch < (ncol >> 5); ++ch) {
             const int c0 = cbase + 32 * ch;
-            ca.mword_in = 0xFFFFFFFFu;
-            if (kMode == 1 && g.relu) ca.mword_in = valid ? mask_row[c0 >> 5] : 0u;
+            ca.mword_in = ch == 0 ? mw[0] : mw[1];
             ca.mword_out = (kMode == 0 && mask_row && valid) ? mask_row + (c0 >> 5) : nullptr;
-            ca.out_rows = out_rows ? out_rows + c0 : nullptr;
             ca.tmem_hi = tmem + lane_base + kColAhi + c0;
             ca.tmem_lo = tmem + lane_base + kColAlo + c0;
             uint32_t v[32];
@@ -513,8 +539,14 @@ mlp_chain_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ bl
         }
         const long long t4 = clock64();
         t_st += t4 - t3;
+        if (training) fence_proxy_async();  // staging tile written through the generic proxy, read by the bulk copy
+        if (training || (kMode == 0 && hsel >= 0)) epi_bar256();  // staging tile complete / head partials in s_hpart
+        if (training && tid == 0) {
+          const int64_t rows_tile = P - p0 < kTileRows ? P - p0 : kTileRows;
+          float* dst = (kMode == 0 ? stash : gstash) + (size_t)P * g.cum_n + (size_t)p0 * g.n;
+          bulk_s2g(dst, staging, (uint32_t)(rows_tile * g.n * 4));
+        }
         if (kMode == 0 && hsel >= 0) {
-          epi_bar256();  // the other half's partial dot products are in s_hpart
           if (half == 0 && valid) {
             const float4 o = *reinterpret_cast<const float4*>(s_hpart + (hsel * 128 + row) * 4);
             const float tot[4] = {hacc[0] + o.x + s_headb[hsel * 4 + 0], hacc[1] + o.y + s_headb[hsel * 4 + 1],
@@ -540,6 +572,7 @@ mlp_chain_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ bl
     }
   }
 
+  if (tid == 0) bulk_wait_all();
   tc_fence_before();
   __syncthreads();
   if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols));

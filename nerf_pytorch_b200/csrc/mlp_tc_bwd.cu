@@ -105,11 +105,13 @@ mlp_wgrad_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ ra
     // X rows: the producing layer's stashed output (kind 0) or the stashed, zero-padded encoding (kind 1)
     const int xw = head ? g.n : (it.kind == 0 ? p.g[g.src].n : (g.enc_sel ? p.dim_dir_pad : p.dim_xyz_pad));
     const bool on = is_a ? (head ? c == 0 : 4 * c < it.nblk) : (4 * c < it.kblk && 4 * c < xw);
+    // stash / gstash rows are chunk-swizzled (swz_col); d_raw and the stashed encodings are plain
+    const bool swz = is_a ? !head : (head || it.kind == 0);
     const float* src =
-        is_a ? (head ? d_raw : gstash + (size_t)P * g.cum_n + it.n0 + 4 * c)
-             : (head ? stash + (size_t)P * g.cum_n + 4 * c
-                     : (it.kind == 0 ? stash + (size_t)P * p.g[g.src].cum_n + it.k0 + 4 * c
-                                     : stash + (size_t)P * p.enc_cum[g.enc_sel] + 4 * c));
+        is_a ? (head ? d_raw : gstash + (size_t)P * g.cum_n + it.n0)
+             : (head ? stash + (size_t)P * g.cum_n
+                     : (it.kind == 0 ? stash + (size_t)P * p.g[g.src].cum_n + it.k0
+                                     : stash + (size_t)P * p.enc_cum[g.enc_sel]));
     const int ld = is_a ? (head ? 4 : g.n) : xw;
     // head items: keep only this head's columns of d_raw
     const float hm0 = (!head || (hcol0 <= 0 && 0 < hcol0 + hcols)) ? 1.f : 0.f;
@@ -127,16 +129,19 @@ mlp_wgrad_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ ra
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int64_t pt = q0 + 4 * (quad0 + 4 * h) + i;
-          float4 t4 = (on && pt < pt_end) ? __ldg(reinterpret_cast<const float4*>(src + (size_t)pt * ld)) : zero4;
+          const int cc = swz ? (c ^ (int)(pt & 7)) : c;
+          float4 t4 = (on && pt < pt_end) ? __ldg(reinterpret_cast<const float4*>(src + (size_t)pt * ld + 4 * cc)) : zero4;
           if (head && is_a) { t4.x *= hm0; t4.y *= hm1; t4.z *= hm2; t4.w *= hm3; }
           v[4 * h + i] = t4;
         }
     };
+    float4 nx1[8];  // two stages of loads in flight per thread (HBM latency x bandwidth needs ~45 KB per SM)
     issue_loads(pt_begin, cur);
+    issue_loads(pt_begin + kStagePts, nx1);
     for (int64_t s = 0; s < n_stage; ++s) {
       const int64_t q0 = pt_begin + s * kStagePts;
       float4 nxt[8];
-      if (s + 1 < n_stage) issue_loads(q0 + kStagePts, nxt);  // keep the next stage's loads in flight
+      issue_loads(q0 + 2 * kStagePts, nxt);  // out-of-range points load zeros
       mbar_wait(&bar_empty[stage], phase ^ 1);
       uint8_t* st = sm + stage * kStageBytesW;
       if (on) {
@@ -161,7 +166,7 @@ mlp_wgrad_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ ra
       mbar_arrive(&bar_full[stage]);
       if (++stage == kStagesW) { stage = 0; phase ^= 1; }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) cur[j] = nxt[j];
+      for (int j = 0; j < 8; ++j) { cur[j] = nx1[j]; nx1[j] = nxt[j]; }
     }
     if (it.bias && is_a && on) {
       if (head) {

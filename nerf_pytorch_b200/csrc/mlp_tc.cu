@@ -607,7 +607,7 @@ static int launch_chain(const Plan& p, const float* blob, const float* rays, int
   int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes), what);
   if (rc) return rc;
   kern<<<grid, kThreadsTc, bytes, s>>>(p, blob, rays, ray_stride, z, P, n_samples, tiles, raw, stash, gstash,
-                                       kMode == 0 ? g_tc_prof : nullptr, g_tc_flags);
+                                       g_tc_prof, g_tc_flags);
   count_launch();
   return check_cuda(cudaGetLastError(), what);
 }

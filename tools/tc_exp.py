@@ -27,3 +27,17 @@ for flags, name, st in ((0, "normal", False), (2, "no MMAs", False), (0, "normal
     pr = prof.view(148, 8).double().mean(0) / 41.5
     print(f"A0 fwd S=192 [{name}]: {t:.3f} ms  per tile: prologue {pr[0]:.0f} wait-mma {pr[1]:.0f} epilogue {pr[2]:.0f} total {pr[3]:.0f} | per layer: tmem-ld {pr[4]/6:.0f} chunks {pr[5]/6:.0f} st-wait {pr[6]/6:.0f} head/bar {pr[7]/6:.0f}")
 lib.nerfb200_debug_tc_flags(0)
+
+# dgrad breakdown (A1, fine pass)
+arch1 = ops.ArchSpec(n_freq_xyz=10, n_freq_dir=4, num_layers=8, hidden=128, skip_every=3)
+blob1 = ops.pack_weights(arch1, torch.randn(arch1.flat_param_count(), device="cuda") * 0.05)
+raw, stash = ops.mlp_fwd(arch1, blob1, rays, z, impl=1, want_stash=True)
+pr = prof.view(148, 8).double().mean(0) / 41.5
+print(f"A1 fwd+stash per tile: prologue {pr[0]:.0f} wait-mma {pr[1]:.0f} epilogue {pr[2]:.0f} total {pr[3]:.0f} | per layer(10): tmem-ld {pr[4]/10:.0f} chunks {pr[5]/10:.0f} st-wait {pr[6]/10:.0f} head/bar {pr[7]/10:.0f}")
+G = torch.randn_like(raw)
+for flags in (0, 2):
+    lib.nerfb200_debug_tc_flags(flags)
+    t = timeit(lambda: ops.mlp_bwd(arch1, blob1, rays, z, G, stash, impl=1), n=5)
+    pr = prof.view(148, 8).double().mean(0) / 41.5
+    print(f"A1 bwd flags={flags}: {t:.3f} ms; dgrad per tile: prologue {pr[0]:.0f} wait-mma {pr[1]:.0f} epilogue {pr[2]:.0f} total {pr[3]:.0f} | per layer(10): tmem-ld {pr[4]/10:.0f} chunks {pr[5]/10:.0f} st-wait {pr[6]/10:.0f} head/bar {pr[7]/10:.0f}")
+lib.nerfb200_debug_tc_flags(0)

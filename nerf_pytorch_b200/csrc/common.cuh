@@ -103,6 +103,7 @@ int launch_adam(float* p, const float* g, float* m, float* v, int64_t n, int ste
 // tcgen05 path (mlp_tc.cu)
 void set_tc_profile(void* p);
 void set_tc_flags(int f);
+int get_tc_flags();
 int launch_mlp_fwd_tc(const Plan& p, const float* blob, const float* rays, int ray_stride, const float* z,
                       int64_t n_rays, int n_samples, float* raw, float* stash, cudaStream_t s);
 

@@ -29,6 +29,7 @@ static long long* g_tc_prof = nullptr;  // debug hook: per-CTA cycle counters (n
 void set_tc_profile(void* p) { g_tc_prof = static_cast<long long*>(p); }
 static int g_tc_flags = 0;  // debug: 1 = skip the weight copies, 2 = skip the MMAs (timing experiments only)
 void set_tc_flags(int f) { g_tc_flags = f; }
+int get_tc_flags() { return g_tc_flags; }
 
 namespace tc {
 constexpr int kEpiThreads = 256;

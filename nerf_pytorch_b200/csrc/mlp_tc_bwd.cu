@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(kThreadsW, 1)
 mlp_wgrad_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ rays, int ray_stride,
                     const float* __restrict__ z, int S, const float* __restrict__ stash,
                     const float* __restrict__ gstash, const float* __restrict__ d_raw, int64_t P,
-                    float* __restrict__ flat_grad, int n_items) {
+                    float* __restrict__ flat_grad, int n_items, int dbg) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + kStagesW * kStageBytesW);
@@ -130,18 +130,15 @@ mlp_wgrad_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ ra
         for (int i = 0; i < 4; ++i) {
           const int64_t pt = q0 + 4 * (quad0 + 4 * h) + i;
           const int cc = swz ? (c ^ (int)(pt & 7)) : c;
-          float4 t4 = (on && pt < pt_end) ? __ldg(reinterpret_cast<const float4*>(src + (size_t)pt * ld + 4 * cc)) : zero4;
-          if (head && is_a) { t4.x *= hm0; t4.y *= hm1; t4.z *= hm2; t4.w *= hm3; }
-          v[4 * h + i] = t4;
+          // (no arithmetic on the loaded value here: it must stay in flight until the stage is built)
+          v[4 * h + i] = (on && pt < pt_end) ? __ldg(reinterpret_cast<const float4*>(src + (size_t)pt * ld + 4 * cc)) : zero4;
         }
     };
-    float4 nx1[8];  // two stages of loads in flight per thread (HBM latency x bandwidth needs ~45 KB per SM)
     issue_loads(pt_begin, cur);
-    issue_loads(pt_begin + kStagePts, nx1);
     for (int64_t s = 0; s < n_stage; ++s) {
       const int64_t q0 = pt_begin + s * kStagePts;
       float4 nxt[8];
-      issue_loads(q0 + 2 * kStagePts, nxt);  // out-of-range points load zeros
+      issue_loads(q0 + kStagePts, nxt);  // keep the next stage's loads in flight (out-of-range points load zeros)
       mbar_wait(&bar_empty[stage], phase ^ 1);
       uint8_t* st = sm + stage * kStageBytesW;
       if (on) {
@@ -149,7 +146,13 @@ mlp_wgrad_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ ra
         uint8_t* lo_b = hi_b + kOpBytes;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          const float4 r0 = cur[4 * h + 0], r1 = cur[4 * h + 1], r2 = cur[4 * h + 2], r3 = cur[4 * h + 3];
+          float4 r0 = cur[4 * h + 0], r1 = cur[4 * h + 1], r2 = cur[4 * h + 2], r3 = cur[4 * h + 3];
+          if (head && is_a) {  // keep only this head's columns of d_raw
+            r0.x *= hm0; r1.x *= hm0; r2.x *= hm0; r3.x *= hm0;
+            r0.y *= hm1; r1.y *= hm1; r2.y *= hm1; r3.y *= hm1;
+            r0.z *= hm2; r1.z *= hm2; r2.z *= hm2; r3.z *= hm2;
+            r0.w *= hm3; r1.w *= hm3; r2.w *= hm3; r3.w *= hm3;
+          }
           // slab (quad) -> [feature/8][feature%8][4 points]; this thread owns 4 consecutive features = 64 B
           const int off = (quad0 + 4 * h) * kSlabW + (c >> 1) * kSboW + (c & 1) * 64;
           split_store(hi_b, lo_b, off + 0, make_float4(r0.x, r1.x, r2.x, r3.x));
@@ -166,7 +169,7 @@ mlp_wgrad_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ ra
       mbar_arrive(&bar_full[stage]);
       if (++stage == kStagesW) { stage = 0; phase ^= 1; }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { cur[j] = nx1[j]; nx1[j] = nxt[j]; }
+      for (int j = 0; j < 8; ++j) cur[j] = nxt[j];
     }
     if (it.bias && is_a && on) {
       if (head) {
@@ -268,7 +271,7 @@ int launch_wgrad_tc(const Plan& p, const float* rays, int ray_stride, const floa
   if (split < 1) split = 1;
   dim3 grid(split, items);
   mlp_wgrad_tc_kernel<<<grid, kThreadsW, bytes, s>>>(p, rays, ray_stride, z, n_samples, stash, gstash, d_raw, P,
-                                                     flat_grad, items);
+                                                     flat_grad, items, get_tc_flags());
   count_launch();
   return check_cuda(cudaGetLastError(), "wgrad_tc launch");
 }

@@ -275,15 +275,18 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)   # max over ranks
         return ms.item()
 
-    for _ in range(max(args.warmup, 3)):
-        step(ro, rd, tgt)
     sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.start()   # nvidia-smi needs a few hundred ms for its first sample: start before the warm-up
+    for _ in range(max(args.warmup, 3)):
+        step(ro, rd, tgt)
+    torch.cuda.synchronize()
+    if rank == 0:
+        time.sleep(0.3)
+        sampler.rows.clear()  # keep only samples taken from here on (timed region)
     l0 = ops.launch_count()
     total_ms = timed(lambda: step(ro, rd, tgt), args.steps)
     launches = (ops.launch_count() - l0) // args.steps
-    clocks = sampler.stop() if rank == 0 else None
     ms_per_step = total_ms / args.steps
     value = RAYS_PER_GPU * world / (ms_per_step / 1e3)
 
@@ -293,6 +296,7 @@ def run_ours(args):
     for _ in range(3):
         fwd_only()
     fwd_ms = timed(fwd_only, args.steps) / args.steps
+    clocks = sampler.stop() if rank == 0 else None   # sampled across the three timed loops (train, e2e, forward)
 
     # ---- roofline of the dominant kernels, timed alone with CUDA events on this stream ----
     roof = roof_bwd = None

@@ -16,6 +16,9 @@ d = torch.randn(N, 3, device="cuda"); d[:, 2] = -1
 o = torch.tensor([[0.0, -2.0, 3.4]], device="cuda").expand(N, 3)
 rays = torch.cat([o, d, torch.full((N, 1), 2.0, device="cuda"), torch.full((N, 1), 6.0, device="cuda"), d / d.norm(dim=-1, keepdim=True)], -1).contiguous()
 z = torch.sort(torch.rand(N, S, device="cuda") * 4 + 2, -1).values.contiguous()
+if os.environ.get("STASH", "1") == "0":
+    for _ in range(3):
+        ops.mlp_fwd(arch, blob, rays, z, impl=impl)
 for _ in range(3):
     raw, stash = ops.mlp_fwd(arch, blob, rays, z, impl=impl, want_stash=True)
 G = torch.randn_like(raw)

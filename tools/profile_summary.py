@@ -45,6 +45,18 @@ for r in rr[2:]:
             d[w] = r[i] + (" " + units[i] if units[i] and w != "Kernel Name" else "")
     summ.append(d)
 json.dump(summ, open(os.path.join(out_dir, f"{tag}_ncu_full_summary.json"), "w"), indent=1)
+# bench.py's roofline.traffic: DRAM bytes of the FIRST captured forward chain launch (inference-mode fine pass)
+def gb(x):
+    v, u = x.split()
+    return float(v) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[u]
+for d in summ:
+    if "mlp_chain_tc_kernel<0>" in d.get("Kernel Name", "") and len(sys.argv) > 4:
+        tr = gb(d["dram__bytes_read.sum"]) + gb(d["dram__bytes_write.sum"])
+        path = os.path.join(out_dir, "r1_ncu_summary.json")
+        cur = json.load(open(path)) if os.path.exists(path) else {}
+        cur[sys.argv[4]] = tr
+        json.dump(cur, open(path, "w"), indent=1)
+        break
 print(open(os.path.join(out_dir, f"{tag}_launch_shares.csv")).read()[:1500])
 for d in summ:
     print({k.split(".")[0][-28:]: v for k, v in d.items()})

@@ -212,9 +212,13 @@ mlp_chain_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ bl
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + Smem::bars);
   uint64_t* bar_full = bars;                      // [kMaxStages]  weights landed
   uint64_t* bar_empty = bars + kMaxStages;        // [kMaxStages]  stage consumed by the MMAs
-  uint64_t* bar_a = bars + 2 * kMaxStages;        // A operand of the next layer is ready (256 arrivals)
-  uint64_t* bar_acc = bars + 2 * kMaxStages + 1;  // accumulator of the current layer is complete
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 2);
+  // A operand of the next layer: columns [0,64) ready AND the accumulator fully drained into registers (bar_a1),
+  // columns [64,128) ready (bar_a2).  The next layer's first 8 k-steps only need the former, so they run while the
+  // epilogue is still working on the second half of its columns.
+  uint64_t* bar_a1 = bars + 2 * kMaxStages;
+  uint64_t* bar_a2 = bars + 2 * kMaxStages + 1;
+  uint64_t* bar_acc = bars + 2 * kMaxStages + 2;  // accumulator of the current layer is complete
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 3);
   const bool training = kMode == 1 || stash != nullptr;
   const uint32_t n_stages = kMaxStages;
   uint8_t* staging = sm + Smem::stage;
@@ -226,7 +230,8 @@ mlp_chain_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ bl
       mbar_init(&bar_full[i], 1);
       mbar_init(&bar_empty[i], 1);
     }
-    mbar_init(bar_a, kEpiThreads);
+    mbar_init(bar_a1, kEpiThreads);
+    mbar_init(bar_a2, kEpiThreads);
     mbar_init(bar_acc, 1);
     fence_barrier_init();
   }
@@ -301,10 +306,15 @@ mlp_chain_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ bl
           const uint32_t slab_b = 16u * n_mma;  // bytes of one weight slab
           const int ksteps = (kMode == 0 ? g.k_tc : g.n) >> 3;
           const int ksteps_h = kMode == 0 ? (g.k_h >> 3) : ksteps;  // k-steps whose A operand is in tensor memory
-          mbar_wait(bar_a, a_phase);
-          a_phase ^= 1;
+          mbar_wait(bar_a1, a_phase);
           tc_fence_after();
+          bool second = false;  // bar_a2 of this layer consumed?
           for (int ks0 = 0; ks0 < ksteps; ks0 += kStepsPerStage) {
+            if (!second && ks0 + kStepsPerStage > 8) {  // this stage touches A columns >= 64 (or the encodings)
+              mbar_wait(bar_a2, a_phase);
+              tc_fence_after();
+              second = true;
+            }
             mbar_wait(&bar_full[pp.stage], pp.phase);
             tc_fence_after();
             const uint32_t wb0 = smem_u32(sm + Smem::ring + pp.stage * kStageBytes);
@@ -337,6 +347,8 @@ mlp_chain_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ bl
             __syncwarp();
             pp.advance(n_stages);
           }
+          if (!second) mbar_wait(bar_a2, a_phase);  // keep the phases aligned for short layers
+          a_phase ^= 1;
           if (elect_one()) mma_commit(bar_acc);  // accumulator of this layer complete
           __syncwarp();
         }
@@ -448,7 +460,8 @@ mlp_chain_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ bl
             for (int k = 0; k < (p.dim_dir_pad >> 2); ++k) __stcs(sd + k, se[k]);
           }
         }
-        mbar_arrive(bar_a);
+        mbar_arrive(bar_a1);
+        mbar_arrive(bar_a2);
       } else {
         const float4 d4 = valid ? reinterpret_cast<const float4*>(raw)[pt] : make_float4(0.f, 0.f, 0.f, 0.f);
         dr[0] = d4.x; dr[1] = d4.y; dr[2] = d4.z; dr[3] = d4.w;
@@ -470,8 +483,6 @@ mlp_chain_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ bl
         const int hcol = hsel >= 0 ? p.h[hsel].out_col : 0;
         float hacc[4] = {0.f, 0.f, 0.f, 0.f};
         const bool is_dir = kMode == 0 && p.use_viewdirs && t == p.n_gemm - 1;
-        const int ncol = g.n >> 1;          // columns of this thread's half
-        const int cbase = half * ncol;
         // training side outputs / inputs of this layer
         uint32_t* mask_row = nullptr;
         if (kMode == 0 ? (stash != nullptr) : (g.relu != 0))
@@ -480,8 +491,8 @@ mlp_chain_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ bl
         // dgrad: fetch this row's ReLU mask words now so that their latency hides behind the MMA wait
         uint32_t mw[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};
         if (kMode == 1 && g.relu) {
-          mw[0] = valid ? __ldg(mask_row + (cbase >> 5)) : 0u;
-          mw[1] = (valid && ncol == 64) ? __ldg(mask_row + (cbase >> 5) + 1) : 0u;
+          mw[0] = valid ? __ldg(mask_row + half) : 0u;                       // columns [32*half, +32)
+          mw[1] = (valid && g.n == 128) ? __ldg(mask_row + 2 + half) : 0u;     // columns [64 + 32*half, +32)
         }
         t0 = clock64();
         if (has_mma) {
@@ -509,21 +520,36 @@ mlp_chain_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ bl
           ca.has_next = has_next;
           ca.row7 = row & 7;
           ca.stg_row = train ? staging + (size_t)row * g.n * 4 : nullptr;
-          for (int ch = 0; ch < (ncol >> 5); ++ch) {
-            const int c0 = cbase + 32 * ch;
-            ca.mword_in = ch == 0 ? mw[0] : mw[1];
-            ca.mword_out = (kMode == 0 && mask_row && valid) ? mask_row + (c0 >> 5) : nullptr;
-            ca.tmem_hi = tmem + lane_base + kColAhi + c0;
-            ca.tmem_lo = tmem + lane_base + kColAlo + c0;
-            uint32_t v[32];
-            if (has_mma) {
-              tmem_ld32(tmem + lane_base + kColAcc + c0, v);
-              tmem_wait_ld();
-            } else {
+          // column chunks of this thread: first [32*half, +32), second [64 + 32*half, +32) (128-wide layers only).
+          // Both are pulled out of the accumulator up front; after the first chunk's A columns are stored the
+          // next layer may start its first 8 k-steps (bar_a1), the second chunk follows under that shadow.
+          const int nch = g.n >> 6;  // 2 for 128-wide layers, 1 for 64-wide ones
+          const int c0a = 32 * half, c0b = 64 + 32 * half;
+          uint32_t v0[32], v1[32];
+          if (has_mma) {
+            tmem_ld32(tmem + lane_base + kColAcc + c0a, v0);
+            if (nch == 2) tmem_ld32(tmem + lane_base + kColAcc + c0b, v1);
+            tmem_wait_ld();
+          } else {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = 0u;
-            }
-            epilogue_chunk_dispatch<kMode>(hsel >= 0, train, v, c0, ca, hacc);
+            for (int j = 0; j < 32; ++j) v0[j] = v1[j] = 0u;
+          }
+          ca.mword_in = mw[0];
+          ca.mword_out = (kMode == 0 && mask_row && valid) ? mask_row + (c0a >> 5) : nullptr;
+          ca.tmem_hi = tmem + lane_base + kColAhi + c0a;
+          ca.tmem_lo = tmem + lane_base + kColAlo + c0a;
+          epilogue_chunk_dispatch<kMode>(hsel >= 0, train, v0, c0a, ca, hacc);
+          if (has_next) {
+            tmem_wait_st();
+            tc_fence_before();
+            mbar_arrive(bar_a1);
+          }
+          if (nch == 2) {
+            ca.mword_in = mw[1];
+            ca.mword_out = (kMode == 0 && mask_row && valid) ? mask_row + (c0b >> 5) : nullptr;
+            ca.tmem_hi = tmem + lane_base + kColAhi + c0b;
+            ca.tmem_lo = tmem + lane_base + kColAlo + c0b;
+            epilogue_chunk_dispatch<kMode>(hsel >= 0, train, v1, c0b, ca, hacc);
           }
         }
         const long long t3 = clock64();
@@ -534,7 +560,7 @@ mlp_chain_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ bl
         if (has_next) {
           tmem_wait_st();
           tc_fence_before();
-          mbar_arrive(bar_a);
+          mbar_arrive(bar_a2);
         } else {
           tc_fence_before();
         }

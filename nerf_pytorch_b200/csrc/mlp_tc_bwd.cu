@@ -19,14 +19,18 @@
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "wgrad_items.cuh"
+#include <cstdlib>
 
 namespace nerfb200 {
 
 namespace tcw {
-constexpr int kThreadsW = 320;               // warps 0-3: A, warps 4-7: B, warp 8: MMA issue + TMEM alloc, warp 9: copies
+constexpr int kThreadsW = 576;               // warps 0-3/8-11: A, 4-7/12-15: B (even/odd stages), 16: MMA + TMEM alloc, 17: copies
+constexpr int kWarpMma = 16;
 constexpr int kStagePts = 32;                // points per pipeline stage = 4 MMA k-groups
-constexpr int kRawStages = 3;                // ring of raw row blocks filled by the copy engine
-constexpr int kOpStages = 3;                 // ring of transposed operands (B in shared memory, A in tensor memory)
+// Both rings have an EVEN number of slots, so a slot always belongs to the same transposer group: a parity wait
+// is only safe if the waiting thread itself consumed the slot's previous phase.
+constexpr int kRawStages = 4;                // ring of raw row blocks filled by the copy engine
+constexpr int kOpStages = 2;                 // ring of transposed operands (B in shared memory, A in tensor memory)
 constexpr int kSboW = 144;                   // 8-feature core matrices 128 B + 16 B pad apart
 constexpr int kSlabW = 16 * kSboW;           // 128 features x 4 points (one K-major slab), padded
 constexpr int kOpBytes = (kStagePts / 4) * kSlabW;  // one B tile (hi or lo): 8 slabs = 18 KB
@@ -52,7 +56,8 @@ __device__ __forceinline__ void split_store(uint8_t* hi_base, uint8_t* lo_base, 
 
 __global__ void __launch_bounds__(kThreadsW, 1)
 mlp_wgrad_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ stash, const float* __restrict__ gstash,
-                    const float* __restrict__ d_raw, int64_t P, float* __restrict__ flat_grad, int n_items) {
+                    const float* __restrict__ d_raw, int64_t P, float* __restrict__ flat_grad,
+                    const __grid_constant__ WgGrid grid) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* raw = sm + kOpStages * kStageBytesW;
@@ -65,8 +70,10 @@ mlp_wgrad_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ st
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_done + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if ((int)blockIdx.y >= n_items) return;
-  const WgItem it = wg_decode(p, blockIdx.y);
+  int item = 0;
+  while (item + 1 < grid.n_items && (int)blockIdx.x >= grid.start[item + 1]) ++item;
+  const int part = (int)blockIdx.x - grid.start[item], parts = grid.start[item + 1] - grid.start[item];
+  const WgItem it = wg_decode(p, item);
   // operand sources.  gemm items: A rows = dY_t (gstash), B rows = the producing layer's output or the stashed
   // encoding.  Head items (fc_alpha / fc_rgb / fc_out): A rows = d_raw[p][0..3] restricted to the head's columns
   // (<= 4 live rows of the 128-row tile), B rows = the output of the layer the head reads.
@@ -74,8 +81,8 @@ mlp_wgrad_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ st
   const GemmLayer& g = p.g[head ? p.h[it.t].src : it.t];
   const int hcol0 = head ? p.h[it.t].out_col : 0, hcols = head ? p.h[it.t].n_out : 0;
   // both sources are dense row-major [P][width] arrays, so 32 consecutive points are ONE contiguous block
-  const int wa = head ? 4 : g.n;  // floats per dY row
-  const int wb = head ? g.n : (it.kind == 0 ? p.g[g.src].n : (g.enc_sel ? p.dim_dir_pad : p.dim_xyz_pad));
+  int wa, wb;  // floats per dY row / per X row
+  wg_row_widths(p, it, &wa, &wb);
   const float* src_a = head ? d_raw : gstash + (size_t)P * g.cum_n;
   const float* src_b = head ? stash + (size_t)P * g.cum_n
                             : (it.kind == 0 ? stash + (size_t)P * p.g[g.src].cum_n
@@ -83,8 +90,8 @@ mlp_wgrad_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ st
 
   // contiguous point range of this CTA, in units of one stage
   const int64_t stages_total = (P + kStagePts - 1) / kStagePts;
-  const int64_t per = (stages_total + gridDim.x - 1) / gridDim.x;
-  int64_t pt_begin = (int64_t)blockIdx.x * per * kStagePts;
+  const int64_t per = (stages_total + parts - 1) / parts;
+  int64_t pt_begin = (int64_t)part * per * kStagePts;
   int64_t pt_end = pt_begin + per * kStagePts;
   if (pt_begin > P) pt_begin = P;
   if (pt_end > P) pt_end = P;
@@ -103,7 +110,7 @@ mlp_wgrad_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ st
     mbar_init(bar_done, 1);
     fence_barrier_init();
   }
-  if (warp == 8) {
+  if (warp == kWarpMma) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)),
                  "r"(kTmemColsW));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
@@ -120,15 +127,20 @@ mlp_wgrad_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ st
   const int n_mma = it.kblk;  // accumulator columns (multiple of 16)
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
 
-  if (warp < 4) {
+  // two transposer groups alternate stages (group 0: warps 0-7, group 1: warps 8-15): the per-stage chain
+  // wait -> shared-memory reads -> split -> tcgen05.st / st.shared -> fence -> arrive is latency-bound for one
+  // warp, so two stages are kept in flight
+  const int grp = warp >> 3, wg = warp & 7;
+  if (warp < kWarpMma && wg < 4) {
     // ===================== A: raw dY rows -> tensor memory (lane = feature, column = point) =====================
-    const int n = tid;
+    const int n = tid & 127;
     const bool on_n = head ? (n >= hcol0 && n < hcol0 + hcols) : (n < it.nblk && n < wa);
-    const uint32_t lane_base = ((uint32_t)(warp * 32)) << 16;
+    const uint32_t lane_base = ((uint32_t)(wg * 32)) << 16;
     const int row_b = wa * 4;
     float bsum = 0.f;
-    uint32_t rs = 0, rph = 0, os = 0, oph = 0;
-    for (int64_t s = 0; s < n_stage; ++s) {
+    for (int64_t s = grp; s < n_stage; s += 2) {
+      const uint32_t rs = (uint32_t)(s % kRawStages), rph = (uint32_t)(s / kRawStages) & 1u;
+      const uint32_t os = (uint32_t)(s % kOpStages), oph = (uint32_t)(s / kOpStages) & 1u;
       const int rows = (int)min((int64_t)kStagePts, pt_end - (pt_begin + s * kStagePts));
       uint32_t hi[32], lo[32];
       mbar_wait(&raw_full[rs], rph);
@@ -151,15 +163,14 @@ mlp_wgrad_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ st
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&raw_empty[rs]);
-      if (++rs == kRawStages) { rs = 0; rph ^= 1; }
       mbar_wait(&op_empty[os], oph ^ 1);
+      __syncwarp();  // (the spin loops above may leave the warp diverged; tcgen05.st is .sync.aligned)
       tc_fence_after();
       tmem_st32(tmem + lane_base + kColA + 64 * os, hi);
       tmem_st32(tmem + lane_base + kColA + 64 * os + 32, lo);
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(&op_full[os]);
-      if (++os == kOpStages) { os = 0; oph ^= 1; }
     }
     if (it.bias && on_n) {
       float* gb = head ? flat_grad + p.h[it.t].flat_b + (n - hcol0) : flat_grad + g.flat_b + it.n0 + n;
@@ -167,13 +178,14 @@ mlp_wgrad_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ st
     }
     // ===================== drain the accumulator (TMEM lane = output row n) =====================
     mbar_wait(bar_done, 0);
+    __syncwarp();
     tc_fence_after();
     const int in_real = head ? p.h[it.t].k : g.k_h + g.enc_real;
     const int coff = head ? 0 : (it.kind == 0 ? it.k0 : g.k_h);
     const int kreal = head ? p.h[it.t].k : (it.kind == 0 ? it.kblk : g.enc_real);
     float* dst = head ? flat_grad + p.h[it.t].flat_w + (size_t)(n - hcol0) * in_real
                       : flat_grad + g.flat_w + (size_t)(it.n0 + n) * in_real + coff;
-    for (int c0 = 0; c0 < n_mma; c0 += 32) {
+    for (int c0 = 32 * grp; c0 < n_mma; c0 += 64) {  // the two groups share the drain
       uint32_t v[32];
       if (n_mma - c0 >= 32) {
         tmem_ld32(tmem + lane_base + kColAccW + c0, v);
@@ -197,15 +209,16 @@ mlp_wgrad_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ st
       }
     }
     tc_fence_before();
-  } else if (warp < 8) {
+  } else if (warp < kWarpMma) {
     // ===================== B: raw X rows -> K-major hi/lo slabs.  lane = 4-feature chunk, warp = point quad =====
     const int c = lane;               // features 4c .. 4c+3
     const int quad0 = warp & 3;       // this thread transposes quads quad0 and quad0 + 4 of every stage
     const bool on = 4 * c < it.kblk && 4 * c < wb;
     const bool swz = head || it.kind == 0;  // layer outputs are chunk-swizzled, the stashed encodings are plain
     const int row_b = wb * 4;
-    uint32_t rs = 0, rph = 0, os = 0, oph = 0;
-    for (int64_t s = 0; s < n_stage; ++s) {
+    for (int64_t s = grp; s < n_stage; s += 2) {
+      const uint32_t rs = (uint32_t)(s % kRawStages), rph = (uint32_t)(s / kRawStages) & 1u;
+      const uint32_t os = (uint32_t)(s % kOpStages), oph = (uint32_t)(s / kOpStages) & 1u;
       const int rows = (int)min((int64_t)kStagePts, pt_end - (pt_begin + s * kStagePts));
       float4 v[8];
       mbar_wait(&raw_full[rs], rph);
@@ -223,7 +236,6 @@ mlp_wgrad_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ st
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&raw_empty[rs]);
-      if (++rs == kRawStages) { rs = 0; rph ^= 1; }
       mbar_wait(&op_empty[os], oph ^ 1);
       if (on) {
         uint8_t* hi_b = sm + os * kStageBytesW;
@@ -241,9 +253,8 @@ mlp_wgrad_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ st
       }
       fence_proxy_async();
       mbar_arrive(&op_full[os]);
-      if (++os == kOpStages) { os = 0; oph ^= 1; }
     }
-  } else if (warp == 8) {
+  } else if (warp == kWarpMma) {
     // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
     const uint32_t idesc = make_idesc(n_mma);
     uint32_t os = 0, oph = 0;
@@ -290,7 +301,7 @@ mlp_wgrad_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ st
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemColsW));
+  if (warp == kWarpMma) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemColsW));
 }
 
 int launch_wgrad_tc(const Plan& p, const float* rays, int ray_stride, const float* z, int64_t n_rays, int n_samples,
@@ -309,12 +320,40 @@ int launch_wgrad_tc(const Plan& p, const float* rays, int ray_stride, const floa
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  // two full waves of one-CTA-per-SM.  The kernel streams every operand row from HBM exactly once, so an item's
+  // time is its bytes per point: hand each item CTAs in proportion, and all CTAs finish together.
+  if (items > kWgMaxItems) {
+    set_error("wgrad impl=1 (tcgen05): %d work items exceed the grid table (%d)", items, kWgMaxItems);
+    return NERFB200_ERR_UNSUPPORTED;
+  }
   const int64_t stages = (P + kStagePts - 1) / kStagePts;
-  int split = (2 * sms) / items;  // two full waves of one-CTA-per-SM, no ragged third wave
-  if (split > stages) split = (int)stages;
-  if (split < 1) split = 1;
-  dim3 grid(split, items);
-  mlp_wgrad_tc_kernel<<<grid, kThreadsW, bytes, s>>>(p, stash, gstash, d_raw, P, flat_grad, items);
+  int budget = ((2 * sms) / items) * items;  // equal shares line the items' point ranges up (shared rows hit L2)
+  if (budget < items) budget = items;
+  int cost[kWgMaxItems], total = 0;
+  for (int i = 0; i < items; ++i) {
+    int wa, wb;
+    const WgItem it = wg_decode(p, i);
+    wg_row_widths(p, it, &wa, &wb);
+    // (narrow-A items are bound by their 12 MMAs per stage instead: ~5/8 of the HBM time of a 256-float item)
+    const char* e = getenv("NERFB200_WG_FLOOR");
+    const int mma_cost = e ? atoi(e) : 1 << 20;  // default: equal shares
+    (void)it;
+    cost[i] = wa + wb > mma_cost ? wa + wb : mma_cost;
+    total += cost[i];
+  }
+  WgGrid grid;
+  grid.n_items = items;
+  grid.start[0] = 0;
+  int acc_cost = 0;
+  for (int i = 0; i < items; ++i) {
+    // cumulative rounding keeps the sum at exactly `budget`; every item gets at least one CTA
+    acc_cost += cost[i];
+    int end = (int)(((int64_t)budget * acc_cost + total / 2) / total);
+    if (end < grid.start[i] + 1) end = grid.start[i] + 1;
+    if (end - grid.start[i] > stages) end = grid.start[i] + (int)stages;
+    grid.start[i + 1] = (short)end;
+  }
+  mlp_wgrad_tc_kernel<<<grid.start[items], kThreadsW, bytes, s>>>(p, stash, gstash, d_raw, P, flat_grad, grid);
   count_launch();
   return check_cuda(cudaGetLastError(), "wgrad_tc launch");
 }

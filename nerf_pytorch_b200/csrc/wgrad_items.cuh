@@ -23,7 +23,9 @@ __host__ __device__ inline int wg_item_count(const Plan& p) {
   return n + p.n_head;
 }
 
-__device__ inline WgItem wg_decode(const Plan& p, int item) {
+__host__ __device__ inline int wg_imin(int a, int b) { return a < b ? a : b; }
+
+__host__ __device__ inline WgItem wg_decode(const Plan& p, int item) {
   WgItem it;
   for (int t = 0; t < p.n_gemm; ++t) {
     const GemmLayer& g = p.g[t];
@@ -34,11 +36,11 @@ __device__ inline WgItem wg_decode(const Plan& p, int item) {
       const int bn = item / per, bk = item - bn * per;
       it.t = t;
       it.n0 = bn * 128;
-      it.nblk = min(128, g.n - it.n0);
+      it.nblk = wg_imin(128, g.n - it.n0);
       if (bk < kb) {
         it.kind = 0;
         it.k0 = bk * 128;
-        it.kblk = min(128, g.k_h - it.k0);
+        it.kblk = wg_imin(128, g.k_h - it.k0);
         it.bias = (bk == 0);
       } else {
         it.kind = 1;
@@ -55,5 +57,24 @@ __device__ inline WgItem wg_decode(const Plan& p, int item) {
   it.n0 = 0; it.nblk = p.h[item].n_out; it.k0 = 0; it.kblk = p.h[item].k; it.bias = 1;
   return it;
 }
+
+// floats one point costs an item in the tcgen05 kernel: one dY row + one X row (both read from HBM exactly once)
+__host__ __device__ inline void wg_row_widths(const Plan& p, const WgItem& it, int* wa, int* wb) {
+  if (it.kind == 2) {
+    *wa = 4;
+    *wb = p.g[p.h[it.t].src].n;
+  } else {
+    const GemmLayer& g = p.g[it.t];
+    *wa = g.n;
+    *wb = it.kind == 0 ? p.g[g.src].n : (g.enc_sel ? p.dim_dir_pad : p.dim_xyz_pad);
+  }
+}
+
+constexpr int kWgMaxItems = 32;
+// CTA -> (item, part) map of the tcgen05 kernel: item i owns CTAs [start[i], start[i+1]), sized by its HBM bytes
+struct WgGrid {
+  int n_items;
+  short start[kWgMaxItems + 1];
+};
 
 }  // namespace nerfb200

@@ -21,8 +21,7 @@ rays = torch.cat([o, d, torch.full((N, 1), 2.0, device="cuda"), torch.full((N, 1
 z = torch.sort(torch.rand(N, S, device="cuda") * 4 + 2, -1).values.contiguous()
 raw, stash = ops.mlp_fwd(arch, blob, rays, z, impl=1, want_stash=True)
 G = torch.randn_like(raw)
-for flags, name in ((0, "normal"), (16, "no swizzle (wrong data)"), (32, "one wave"), (48, "both")):
-    lib.nerfb200_debug_tc_flags(flags)
-    t = timeit(lambda: ops.mlp_bwd(arch, blob, rays, z, G, stash, impl=1))
-    print(f"A1 bwd [{name}]: {t:.3f} ms")
-lib.nerfb200_debug_tc_flags(0)
+for floor in (64, 128, 160, 192, 224, 256, 288):
+    os.environ["NERFB200_WG_FLOOR"] = str(floor)
+    t = timeit(lambda: ops.mlp_bwd(arch, blob, rays, z, G, stash, impl=1), n=10, warm=3)
+    print(f"A1 bwd [floor {floor}]: {t:.3f} ms")

@@ -69,8 +69,12 @@ int64_t nerfb200_launch_count(void);
  * [prologue, wait-for-MMA, epilogue, total, tmem-load, chunk math+stores, tmem-store wait, head] of its
  * epilogue thread 0; NULL switches it off. */
 void nerfb200_debug_tc_profile(void* buf);
-/* debug hook for timing experiments (results are garbage): bit 0 skips the weight copies, bit 1 the MMAs */
+/* debug hook for timing experiments: bit 0 skips the weight copies, bit 1 the MMAs (results are garbage);
+ * bit 2 makes mlp_bwd skip its dgrad launch, bit 3 its wgrad launch (to time the two kernels apart: with bit 2 set
+ * the wgrad kernel consumes the gradient stash a previous full call left in the workspace) */
 void nerfb200_debug_tc_flags(int32_t flags);
+/* HBM bytes the tcgen05 wgrad kernel reads per point: sum over its work items of one dY row + one X row */
+int64_t nerfb200_debug_wgrad_bytes_per_point(const nerfb200_arch_t* arch);
 
 /* ---- parameters -------------------------------------------------------------------------------
  * Canonical order of the linears ("slots"): layer1, layers_xyz[0..num_layers-2], then

@@ -57,6 +57,7 @@ SIGNATURES = {
     "nerfb200_launch_count": (I64, []),
     "nerfb200_debug_tc_profile": (None, [P]),
     "nerfb200_debug_tc_flags": (None, [I32]),
+    "nerfb200_debug_wgrad_bytes_per_point": (I64, [P]),
     "nerfb200_num_linear": (I64, [AP]),
     "nerfb200_flat_param_count": (I64, [AP]),
     "nerfb200_blob_floats": (I64, [AP]),

@@ -7,6 +7,7 @@
 #include <atomic>
 
 #include "common.cuh"
+#include "wgrad_items.cuh"
 
 namespace nerfb200 {
 
@@ -249,6 +250,17 @@ const char* nerfb200_last_error(void) { return g_err; }
 int64_t nerfb200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 void nerfb200_debug_tc_profile(void* buf) { set_tc_profile(buf); }
 void nerfb200_debug_tc_flags(int32_t flags) { set_tc_flags(flags); }
+int64_t nerfb200_debug_wgrad_bytes_per_point(const nerfb200_arch_t* arch) {
+  Plan p;
+  if (build_plan(arch, &p) != NERFB200_OK) return -1;
+  int64_t floats = 0;
+  for (int i = 0, n = wg_item_count(p); i < n; ++i) {
+    int wa, wb;
+    wg_row_widths(p, wg_decode(p, i), &wa, &wb);
+    floats += wa + wb;
+  }
+  return 4 * floats;
+}
 
 int64_t nerfb200_num_linear(const nerfb200_arch_t* arch) {
   Plan p;

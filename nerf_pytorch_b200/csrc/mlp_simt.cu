@@ -654,9 +654,12 @@ int launch_mlp_bwd(const Plan& p, const float* blob, const float* rays, int ray_
                    int64_t n_rays, int n_samples, const float* d_raw, const float* stash, float* gstash,
                    float* flat_grad, int impl, cudaStream_t s) {
   const int64_t P = n_rays * n_samples;
-  int rc = (impl == 1 && p.hidden == 128) ? launch_dgrad_tc(p, blob, d_raw, stash, gstash, P, s)
-                                          : launch_dgrad_simt(p, blob, d_raw, stash, gstash, P, s);
-  if (rc) return rc;
+  const int dbg = get_tc_flags();  // timing experiments only: 4 = no dgrad launch, 8 = no wgrad launch
+  int rc = NERFB200_OK;
+  if (!(dbg & 4))
+    rc = (impl == 1 && p.hidden == 128) ? launch_dgrad_tc(p, blob, d_raw, stash, gstash, P, s)
+                                        : launch_dgrad_simt(p, blob, d_raw, stash, gstash, P, s);
+  if (rc || (dbg & 8)) return rc;
   const int items = wg_item_count(p);
   if (impl == 1 && p.hidden == 128) {
     return launch_wgrad_tc(p, rays, ray_stride, z, n_rays, n_samples, stash, gstash, d_raw, flat_grad, s);

@@ -1,25 +1,28 @@
 // mlp_tc_bwd.cu -- tcgen05 weight-gradient kernel:  dW[n][k] = sum_p dY[p][n] * X[p][k]   (3xTF32)
 //
-// One CTA = one (layer, row-block, column-block) item of wgrad_items.cuh -- the 1..4-row heads included -- over
-// a contiguous range of points.  The reduction runs over POINTS while the stash rows dY[p][:] / X[p][:] are
-// feature-contiguous, so both operands are transposed on the way in, 32 points per pipeline stage:
-//   A = dY^T (M = 128 output features) lives in TENSOR MEMORY (lane = feature, column = point).  Warps 0-3 copy
-//       the 32 rows raw into a 16 KB shared-memory tile (coalesced float4 loads, conflict-free stores), then each
-//       thread reads ITS feature of the 32 points back (conflict-free 4-byte loads: the stash chunk swizzle is a
-//       permutation inside each 128-byte segment), splits hi/lo and writes both halves with two tcgen05.st.
-//   B = X^T (N = 128|64|32.. input features) stays in shared memory: warps 4-7 load the same 4 features of 4
-//       consecutive points (float4), transpose the 4x4 block in registers, split hi/lo and store 64 contiguous bytes
-//       per operand into the UMMA canonical K-major no-swizzle layout (slab = [feature][4 points], core matrices
-//       padded to 144 B apart so the stores are bank-conflict free).
-// One elected lane issues three tcgen05.mma.kind::tf32 per 8 points (hi*hi, lo*hi, hi*lo; A from tensor memory)
-// into a 128 x N fp32 accumulator in tensor memory that lives for the whole point range; at the end four warps
-// drain it with tcgen05.ld and atomically add into the flat gradient.  Per point and layer the kernel reads
-// (n + k) * 4 bytes from HBM once; shared memory sees 32 KB (A) + 32 KB (B writes) + 48 KB (MMA reads of B) per
-// stage instead of the 160 KB of an all-shared-memory formulation, which was bandwidth-bound on it.
+// One CTA = one (layer, row-block, column-block) item of wgrad_items.cuh -- the 1..4-row heads included -- over a
+// contiguous range of points.  The reduction runs over POINTS while the stash rows dY[p][:] / X[p][:] are
+// feature-contiguous, so both operands are transposed on chip, 32 points per pipeline stage:
+//   copy warp    both stashes are dense row-major arrays, so the 32 rows of a stage are ONE contiguous block per
+//                operand: one cp.async.bulk each into a 4-deep ring of raw tiles (mbarrier complete_tx).  128 KB
+//                per SM stay in flight, which is what keeps HBM busy (register prefetch could not).
+//   A = dY^T     (M = 128 output features) lives in TENSOR MEMORY (lane = feature, column = point): every thread
+//                reads ITS feature of the 32 raw rows (conflict-free 4-byte loads: the stash chunk swizzle is a
+//                permutation inside each 128-byte segment), splits hi/lo and writes both with two tcgen05.st.
+//   B = X^T      (N = 128|64|48.. input features) goes to shared memory: float4 reads of 4 features x 4 points,
+//                4x4 register transpose, hi/lo split, 64 contiguous bytes per operand into the UMMA canonical
+//                K-major no-swizzle layout (slab = [feature][4 points], core matrices padded to 144 B apart so the
+//                stores are bank-conflict free).
+//   Two transposer groups (8 warps each) alternate stages: the chain wait -> read -> split -> store -> fence ->
+//   arrive is latency-bound for one warp, so two stages are always being transposed.
+//   MMA warp     three tcgen05.mma.kind::tf32 per 8 points (hi*hi, lo*hi, hi*lo; A from tensor memory) into a
+//                128 x N fp32 accumulator in tensor memory that lives for the whole point range; at the end the
+//                A warps drain it with tcgen05.ld and atomically add into the flat gradient.
+// Per point and item the kernel reads (n + k) * 4 bytes from HBM exactly once; it runs at ~80 % of the measured
+// HBM bandwidth.
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "wgrad_items.cuh"
-#include <cstdlib>
 
 namespace nerfb200 {
 
@@ -320,39 +323,21 @@ int launch_wgrad_tc(const Plan& p, const float* rays, int ray_stride, const floa
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  // two full waves of one-CTA-per-SM.  The kernel streams every operand row from HBM exactly once, so an item's
-  // time is its bytes per point: hand each item CTAs in proportion, and all CTAs finish together.
+  // two full waves of one-CTA-per-SM, every item the same number of CTAs: a stage costs about the same for every
+  // item (measured: shares proportional to bytes per point are 10-30 % slower), and equal shares line the items'
+  // point ranges up, so rows two items share (dY of a layer with a skip input, X of the layer a head reads) are
+  // served from L2 the second time.
   if (items > kWgMaxItems) {
     set_error("wgrad impl=1 (tcgen05): %d work items exceed the grid table (%d)", items, kWgMaxItems);
     return NERFB200_ERR_UNSUPPORTED;
   }
   const int64_t stages = (P + kStagePts - 1) / kStagePts;
-  int budget = ((2 * sms) / items) * items;  // equal shares line the items' point ranges up (shared rows hit L2)
-  if (budget < items) budget = items;
-  int cost[kWgMaxItems], total = 0;
-  for (int i = 0; i < items; ++i) {
-    int wa, wb;
-    const WgItem it = wg_decode(p, i);
-    wg_row_widths(p, it, &wa, &wb);
-    // (narrow-A items are bound by their 12 MMAs per stage instead: ~5/8 of the HBM time of a 256-float item)
-    const char* e = getenv("NERFB200_WG_FLOOR");
-    const int mma_cost = e ? atoi(e) : 1 << 20;  // default: equal shares
-    (void)it;
-    cost[i] = wa + wb > mma_cost ? wa + wb : mma_cost;
-    total += cost[i];
-  }
+  int share = (2 * sms) / items;
+  if (share > stages) share = (int)stages;
+  if (share < 1) share = 1;
   WgGrid grid;
   grid.n_items = items;
-  grid.start[0] = 0;
-  int acc_cost = 0;
-  for (int i = 0; i < items; ++i) {
-    // cumulative rounding keeps the sum at exactly `budget`; every item gets at least one CTA
-    acc_cost += cost[i];
-    int end = (int)(((int64_t)budget * acc_cost + total / 2) / total);
-    if (end < grid.start[i] + 1) end = grid.start[i] + 1;
-    if (end - grid.start[i] > stages) end = grid.start[i] + (int)stages;
-    grid.start[i + 1] = (short)end;
-  }
+  for (int i = 0; i <= items; ++i) grid.start[i] = (short)(i * share);
   mlp_wgrad_tc_kernel<<<grid.start[items], kThreadsW, bytes, s>>>(p, stash, gstash, d_raw, P, flat_grad, grid);
   count_launch();
   return check_cuda(cudaGetLastError(), "wgrad_tc launch");

@@ -1,5 +1,5 @@
 """Turn ncu outputs under gpurun_out/ into the small, committed summaries under profiles/.
-usage: python tools/profile_summary.py <tag> <launches.csv> <full.ncu-rep>"""
+usage: python tools/profile_summary.py <tag> <launches.csv> <full.ncu-rep> [A0|A1]"""
 import collections, csv, json, os, subprocess, sys
 
 tag, launches, rep = sys.argv[1:4]
@@ -49,14 +49,18 @@ json.dump(summ, open(os.path.join(out_dir, f"{tag}_ncu_full_summary.json"), "w")
 def gb(x):
     v, u = x.split()
     return float(v) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[u]
-for d in summ:
-    if "mlp_chain_tc_kernel<0>" in d.get("Kernel Name", "") and len(sys.argv) > 4:
-        tr = gb(d["dram__bytes_read.sum"]) + gb(d["dram__bytes_write.sum"])
-        path = os.path.join(out_dir, "r1_ncu_summary.json")
-        cur = json.load(open(path)) if os.path.exists(path) else {}
-        cur[sys.argv[4]] = tr
-        json.dump(cur, open(path, "w"), indent=1)
-        break
+# bench.py's roofline traffic figures: DRAM bytes of the FIRST captured launch of the forward chain kernel
+# (inference-mode fine pass) and of the wgrad kernel.  argv[4] = architecture tag (A0 | A1)
+if len(sys.argv) > 4:
+    path = os.path.join(out_dir, "r1_ncu_summary.json")
+    cur = json.load(open(path)) if os.path.exists(path) else {}
+    for needle, key in (("mlp_chain_tc_kernel<0>", f"mlp_fwd_tc_{sys.argv[4]}_dram_bytes"),
+                        ("mlp_wgrad_tc_kernel", f"mlp_wgrad_tc_{sys.argv[4]}_dram_bytes")):
+        for d in summ:
+            if needle in d.get("Kernel Name", ""):
+                cur[key] = gb(d["dram__bytes_read.sum"]) + gb(d["dram__bytes_write.sum"])
+                break
+    json.dump(cur, open(path, "w"), indent=1)
 print(open(os.path.join(out_dir, f"{tag}_launch_shares.csv")).read()[:1500])
 for d in summ:
     print({k.split(".")[0][-28:]: v for k, v in d.items()})

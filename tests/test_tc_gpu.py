@@ -65,6 +65,34 @@ def test_tc_ragged_tail_and_sizes():
         assert (r1 - r0).abs().max().item() <= 1e-4 * scale + 1e-5, (n, s, (r1 - r0).abs().max().item(), scale)
 
 
+def test_tc_backward_ragged_sizes():
+    """Point counts that are not multiples of the 32-point wgrad stage / the 128-point tile (partial bulk copies,
+    partial last tile): dgrad + wgrad on tcgen05 vs the fp32 CUDA-core kernels."""
+    from nerf_pytorch_b200 import ops
+
+    for case in ("lego_a0_train", "a1_skip_lindisp"):
+        c = Case(case)
+        arch = _arch(c)
+        blob = ops.pack_weights(arch, ops.flatten_state_dict(arch, c.sd_f, "cuda"))
+        g = torch.Generator().manual_seed(7)
+        for n, s in ((1, 16), (7, 50), (33, 17), (5, 37), (129, 100)):
+            d = torch.randn(n, 3, generator=g)
+            rays = torch.cat([torch.randn(n, 3, generator=g) * 0.1 + torch.tensor([0.0, -2.0, 3.0]), d,
+                              torch.full((n, 1), 2.0), torch.full((n, 1), 6.0), d / d.norm(dim=-1, keepdim=True)],
+                             -1).cuda().contiguous()
+            z = torch.sort(torch.rand(n, s, generator=g) * 4 + 2, -1).values.cuda().contiguous()
+            G = torch.randn(n, s, 4, generator=g).cuda()
+            _, stash = ops.mlp_fwd(arch, blob, rays, z, impl=ops.IMPL_TC, want_stash=True)
+            g0, _ = ops.mlp_bwd(arch, blob, rays, z, G, stash, impl=ops.IMPL_SIMT)
+            g1, _ = ops.mlp_bwd(arch, blob, rays, z, G, stash, impl=ops.IMPL_TC)
+            for lname, w_off, b_off, fin, fout in arch.flat_layout():
+                for off, cnt, what in ((w_off, fin * fout, "weight"), (b_off, fout, "bias")):
+                    a, b = g0[off:off + cnt], g1[off:off + cnt]
+                    scale = a.abs().max().item() + 1e-30
+                    assert (a - b).abs().max().item() <= 1e-4 * scale, (case, n, s, lname, what,
+                                                                        (a - b).abs().max().item(), scale)
+
+
 def test_tc_unsupported_hidden_256_is_refused():
     from nerf_pytorch_b200 import ops
 

@@ -495,6 +495,10 @@ mlp_chain_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ bl
           mw[1] = (valid && g.n == 128) ? __ldg(mask_row + 2 + half) : 0u;     // columns [64 + 32*half, +32)
         }
         t0 = clock64();
+        if (training) {  // the previous layer's bulk store must have finished reading the staging tile; checked
+          if (tid == 0) bulk_wait_read();  // BEFORE the accumulator wait, so this barrier hides under the MMAs
+          epi_bar256();
+        }
         if (has_mma) {
           mbar_wait(bar_acc, acc_phase);
           acc_phase ^= 1;
@@ -502,10 +506,6 @@ mlp_chain_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ bl
         }
         const long long t1 = clock64();
         t_wait += t1 - t0;
-        if (training) {  // the previous layer's bulk store must have finished reading the staging tile
-          if (tid == 0) bulk_wait_read();
-          epi_bar256();
-        }
 
         const long long t2 = clock64();
         t_ld += t2 - t1;

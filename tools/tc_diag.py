@@ -1,3 +1,4 @@
+"""tcgen05 vs fp32 CUDA-core kernels on the golden cases: max errors and fine-pass timings.  Diagnostic only."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))

@@ -1,3 +1,5 @@
+"""Timing experiments on the tcgen05 chain kernels: per-CTA cycle counters (nerfb200_debug_tc_profile) and the
+debug switches of nerfb200_debug_tc_flags (weight copies off / MMAs off).  Diagnostic only, not a bench."""
 import os, sys, ctypes
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)

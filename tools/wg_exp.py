@@ -1,3 +1,4 @@
+"""Fine-pass timing of the backward MLP kernels (dgrad + wgrad, 4096 x 192 points, A1).  Diagnostic only."""
 import os, sys, ctypes
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)

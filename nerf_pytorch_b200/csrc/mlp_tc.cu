@@ -1,10 +1,15 @@
 // mlp_tc.cu -- tcgen05 (5th-generation tensor core) implementation of the two layer-chained kernels
 //   forward : points -> positional encoding -> FlexibleNeRFModel   (nerf/train_utils.py:67, :8-25; nerf/models.py:233-256)
 //   dgrad   : the same chain walked backwards, G_t = (G_s W_s[:, :hidden] + d_raw W_head) (.) relu'(layer t)
-// for hidden_size 128, fp32-faithful through a 3xTF32 split
-//     x * w  ~=  x_hi*w_hi + x_lo*w_hi + x_hi*w_lo        (x_hi = tf32(x), x_lo = x - x_hi, same for w)
+// for hidden_size 128, fp32-faithful through a 3-term split
+//     x * w  ~=  x_hi*w_hi + x_lo*w_hi + x_hi*w_lo
 // accumulated in fp32 in tensor memory (single-pass TF32/BF16 misses the 1e-4
 // bar on the shipped checkpoints; the 3-term split meets it).
+//   forward: fp16 x 2 split (x_hi = fp16(x), x_lo = fp16(x - x_hi): 22 significant bits, products exact in the fp32
+//            accumulator), tcgen05.mma.kind::f16 with K = 16 per instruction -- half the tensor time of tf32.
+//            Activations, encodings and weights of a NeRF sit far inside fp16's range (|v| < 65504, absolute
+//            resolution 3e-8 below 0.125); conversions saturate instead of producing infinities.
+//   dgrad  : 3xTF32 (x_hi = tf32(x), x_lo = x - x_hi): gradients span too many decades for fp16.
 //
 // Persistent kernels, one CTA per SM, 320 threads:
 //   warps 0-7  prologue/epilogue: thread (row = tid % 128, half = tid / 128) owns half of the columns of row
@@ -13,11 +18,12 @@
 //              products, split into tf32 hi + lo and tcgen05.st back into tensor memory as the NEXT layer's A
 //              operand; training outputs (activation stash, ReLU bit mask, gradient stash) leave through a
 //              per-warp swizzled shared-memory transpose so that every global store is a full 128-byte row.
-//   warp 8     MMA issuer: one elected lane, tcgen05.mma.kind::tf32 M=128, N=128|64, K=8, three per k-step;
+//   warp 8     MMA issuer: one elected lane, tcgen05.mma M=128, N=128|64, K=16 (f16) | 8 (tf32), three per k-step;
 //              A from tensor memory (hidden activations / gradients) or shared memory (encodings), B = pre-split
 //              weights from the shared-memory ring (four k-steps per stage).
 //   warp 9     weight producer: one cp.async.bulk per stage from the L2-resident blob, mbarrier complete_tx.
-// Tensor memory (512 columns): [0,128) accumulator, [128,256) A_hi, [256,384) A_lo.
+// Tensor memory (512 columns): [0,128) accumulator, [128,256) A_hi, [256,384) A_lo (forward: 64 columns each,
+// two fp16 per column).
 // The direction encoding enters layers_dir[0] through a per-ray fp32 bias computed on the CUDA cores (it is
 // constant along a ray: SURVEY.md section 7.3 item 5), so that layer contracts over K = 128 only.
 #include "common.cuh"
@@ -40,14 +46,14 @@ constexpr int kStageBytes = kStepsPerStage * 8192;
 constexpr int kSlabBytes = 2048;      // 128 rows x 16 B
 constexpr int kMaxRaysPerTile = 10;
 constexpr uint32_t kTmemCols = 512;
-constexpr uint32_t kColAcc = 0, kColAhi = 128, kColAlo = 256, kColElo = 384;  // E_lo: lo parts of the encodings (64 cols)
+constexpr uint32_t kColAcc = 0, kColAhi = 128, kColAlo = 256;
 
 // Shared memory map (bytes from the 1 KB-aligned base).  The hi parts of the encodings are an SS-mode A operand in
 // shared memory, their lo parts live in tensor memory (columns [384, 448)).  `stage` is the 64 KB stash staging tile:
 // a byte-exact image of one 128-row tile of a stash layer, written by the epilogue and shipped with one
 // cp.async.bulk; its first 32 KB double as the per-warp transpose tiles of the encoding stash.
 struct Smem {
-  static constexpr int e_hi = 0;                               // 16 slabs (K <= 64) x 2 KB   (forward only)
+  static constexpr int e_hi = 0;                               // encodings, fp16: 8 slabs (K <= 64) x 2 KB hi, then 8 slabs lo
   static constexpr int ring = e_hi + 16 * kSlabBytes;          // kMaxStages x 32 KB
   static constexpr int stage = ring + kMaxStages * kStageBytes;  // 64 KB staging tile (training)
   static constexpr int tbuf = stage;                           // 8 warps x 4 KB transpose tiles (encoding stash)
@@ -170,14 +176,22 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int c0, 
           make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
   }
   if (a.has_next) {
-    uint32_t hi[32], lo[32];
+    if (kMode == 0) {  // fp16 x 2: two K-adjacent values per tensor-memory column
+      uint32_t hi[16], lo[16];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      hi[j] = tf32_hi(x[j]);
-      lo[j] = __float_as_uint(x[j] - __uint_as_float(hi[j]));
+      for (int j = 0; j < 16; ++j) split_f16x2(x[2 * j], x[2 * j + 1], hi[j], lo[j]);
+      tmem_st16(a.tmem_hi, hi);
+      tmem_st16(a.tmem_lo, lo);
+    } else {
+      uint32_t hi[32], lo[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        hi[j] = tf32_hi(x[j]);
+        lo[j] = __float_as_uint(x[j] - __uint_as_float(hi[j]));
+      }
+      tmem_st32(a.tmem_hi, hi);
+      tmem_st32(a.tmem_lo, lo);
     }
-    tmem_st32(a.tmem_hi, hi);
-    tmem_st32(a.tmem_lo, lo);
   }
 }
 
@@ -273,7 +287,7 @@ mlp_chain_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ bl
           const GemmLayer& g = p.g[s];
           const uint32_t kbytes = kMode == 0 ? 64u * g.n : 64u * g.k_h;  // one k-step (hi + lo)
           const uint8_t* src = reinterpret_cast<const uint8_t*>(blob + (kMode == 0 ? g.tc_off : g.tcd_off));
-          const int ksteps = (kMode == 0 ? g.k_tc : g.n) >> 3;
+          const int ksteps = kMode == 0 ? (g.k_tc + 15) >> 4 : g.n >> 3;  // forward: fp16, K = 16 per step
           for (int ks = 0; ks < ksteps; ks += kStepsPerStage) {
             const uint32_t bytes = (uint32_t)min(kStepsPerStage, ksteps - ks) * kbytes;
             mbar_wait(&bar_empty[pp.stage], pp.phase ^ 1);
@@ -302,15 +316,16 @@ mlp_chain_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ bl
           if (s < 0) continue;
           const GemmLayer& g = p.g[s];
           const int n_mma = kMode == 0 ? g.n : g.k_h;
-          const uint32_t idesc = make_idesc(n_mma);
+          const uint32_t idesc = kMode == 0 ? make_idesc_f16(n_mma) : make_idesc(n_mma);
           const uint32_t slab_b = 16u * n_mma;  // bytes of one weight slab
-          const int ksteps = (kMode == 0 ? g.k_tc : g.n) >> 3;
-          const int ksteps_h = kMode == 0 ? (g.k_h >> 3) : ksteps;  // k-steps whose A operand is in tensor memory
+          const int ksteps = kMode == 0 ? (g.k_tc + 15) >> 4 : g.n >> 3;
+          const int ksteps_h = kMode == 0 ? (g.k_h >> 4) : ksteps;  // k-steps whose A operand is in tensor memory
+          constexpr int kHalfSteps = kMode == 0 ? 4 : 8;            // k-steps covered by A columns [0, 64)
           mbar_wait(bar_a1, a_phase);
           tc_fence_after();
           bool second = false;  // bar_a2 of this layer consumed?
           for (int ks0 = 0; ks0 < ksteps; ks0 += kStepsPerStage) {
-            if (!second && ks0 + kStepsPerStage > 8) {  // this stage touches A columns >= 64 (or the encodings)
+            if (!second && ks0 + kStepsPerStage > kHalfSteps) {  // this stage touches A columns >= 64 (or the encodings)
               mbar_wait(bar_a2, a_phase);
               tc_fence_after();
               second = true;
@@ -327,18 +342,22 @@ mlp_chain_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ bl
                 const uint64_t b_hi = make_desc(wb, slab_b, 128);
                 const uint64_t b_lo = make_desc(wb + 2 * slab_b, slab_b, 128);
                 const uint32_t acc0 = ks > 0 ? 1u : 0u;
-                if (ks < ksteps_h) {
-                  const uint32_t a_hi = tmem + kColAhi + 8 * ks, a_lo = tmem + kColAlo + 8 * ks;
+                const uint32_t a_hi = tmem + kColAhi + 8 * ks, a_lo = tmem + kColAlo + 8 * ks;
+                if (kMode == 1) {
                   mma_ts(tmem + kColAcc, a_hi, b_hi, idesc, acc0);
                   mma_ts(tmem + kColAcc, a_lo, b_hi, idesc, 1u);
                   mma_ts(tmem + kColAcc, a_hi, b_lo, idesc, 1u);
-                } else {
+                } else if (ks < ksteps_h) {
+                  mma_ts_f16(tmem + kColAcc, a_hi, b_hi, idesc, acc0);
+                  mma_ts_f16(tmem + kColAcc, a_lo, b_hi, idesc, 1u);
+                  mma_ts_f16(tmem + kColAcc, a_hi, b_lo, idesc, 1u);
+                } else {  // encodings: both halves are shared-memory operands (8 slabs hi, 8 slabs lo)
                   const uint32_t off = (uint32_t)(ks - ksteps_h) * 2 * kSlabBytes;
-                  const uint64_t a_hi = make_desc(e_hi + off, kSlabBytes, 128);
-                  const uint32_t a_lo = tmem + kColElo + 8 * (ks - ksteps_h);
-                  mma_ss(tmem + kColAcc, a_hi, b_hi, idesc, acc0);
-                  mma_ts(tmem + kColAcc, a_lo, b_hi, idesc, 1u);
-                  mma_ss(tmem + kColAcc, a_hi, b_lo, idesc, 1u);
+                  const uint64_t e_hi_d = make_desc(e_hi + off, kSlabBytes, 128);
+                  const uint64_t e_lo_d = make_desc(e_hi + 8 * kSlabBytes + off, kSlabBytes, 128);
+                  mma_ss_f16(tmem + kColAcc, e_hi_d, b_hi, idesc, acc0);
+                  mma_ss_f16(tmem + kColAcc, e_lo_d, b_hi, idesc, 1u);
+                  mma_ss_f16(tmem + kColAcc, e_hi_d, b_lo, idesc, 1u);
                 }
               }
             }
@@ -393,13 +412,11 @@ mlp_chain_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ bl
           const int base = p.inc_xyz ? 3 : 0;
           auto put = [&](int k, float v) {
             if (sx) sx[k] = v;
-            const uint32_t hi = tf32_hi(v);
-            const float lo = v - __uint_as_float(hi);
-            const int off = (k >> 2) * kSlabBytes + row * 16 + (k & 3) * 4;
-            *reinterpret_cast<uint32_t*>(e_hi + off) = hi;
-            asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(tmem + lane_base + kColElo + k),
-                         "r"(__float_as_uint(lo))
-                         : "memory");
+            uint32_t hi, lo;
+            split_f16x2(v, 0.f, hi, lo);  // this element in the low halves
+            const int off = (k >> 3) * kSlabBytes + row * 16 + (k & 7) * 2;
+            *reinterpret_cast<uint16_t*>(e_hi + off) = (uint16_t)hi;
+            *reinterpret_cast<uint16_t*>(e_hi + 8 * kSlabBytes + off) = (uint16_t)lo;
           };
           for (int c = 0; c < 3; ++c) {
             const float x = __fadd_rn(rr[c], __fmul_rn(rr[3 + c], zz));  // pts = ro + rd * z (train_utils.py:67)
@@ -411,8 +428,11 @@ mlp_chain_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ bl
               put(base + 6 * f + 3 + c, cs);
             }
           }
-          if (half == 1)
+          if (half == 1) {  // zero padding: the stash row is dim_xyz_pad wide, the operand one fp16 k-step (16) granular
             for (int k = p.dim_xyz; k < p.dim_xyz_pad; ++k) put(k, 0.f);
+            sx = nullptr;
+            for (int k = p.dim_xyz_pad; k < ((p.dim_xyz_pad + 15) & ~15); ++k) put(k, 0.f);
+          }
         }
         // ---- per-ray direction term of layers_dir[0]: vb[ray][n] = sum_k enc_dir(ray)[k] * W[n][H + k]
         if (p.use_viewdirs) {
@@ -431,25 +451,24 @@ mlp_chain_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ bl
             s_viewb[j * 64 + n] = a + s_bias[(p.n_gemm - 1) * 128 + n];  // per-ray bias of layers_dir[0]
           }
         }
-        tmem_wait_st();       // E_lo went to tensor memory
         tc_fence_before();
-        fence_proxy_async();  // E_hi was written through the generic proxy; the MMAs read it via the async proxy
+        fence_proxy_async();  // E was written through the generic proxy; the MMAs read it via the async proxy
         if (training && tid == 0) bulk_wait_read();  // transpose tiles below overlap the staging tile
         epi_bar256();         // also publishes s_viewb
         if (stash) {
           if (p.dim_xyz_pad == 64) {
-            // this thread's row, channels [32*half, 32*half + 32): hi (smem) + lo (tensor memory) is the exact fp32 value
+            // this thread's row, channels [32*half, 32*half + 32): hi + lo is the value the forward contracted with
             float x[32];
-            uint32_t lo32[32];
-            tmem_ld32(tmem + lane_base + kColElo + 32 * half, lo32);
-            tmem_wait_ld();
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const float4 h4 = *reinterpret_cast<const float4*>(e_hi + (8 * half + q) * kSlabBytes + row * 16);
-              x[4 * q] = h4.x + __uint_as_float(lo32[4 * q]);
-              x[4 * q + 1] = h4.y + __uint_as_float(lo32[4 * q + 1]);
-              x[4 * q + 2] = h4.z + __uint_as_float(lo32[4 * q + 2]);
-              x[4 * q + 3] = h4.w + __uint_as_float(lo32[4 * q + 3]);
+            for (int q = 0; q < 4; ++q) {
+              const uint4 h8 = *reinterpret_cast<const uint4*>(e_hi + (4 * half + q) * kSlabBytes + row * 16);
+              const uint4 l8 = *reinterpret_cast<const uint4*>(e_hi + (8 + 4 * half + q) * kSlabBytes + row * 16);
+              const uint32_t hh[4] = {h8.x, h8.y, h8.z, h8.w}, ll[4] = {l8.x, l8.y, l8.z, l8.w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                x[8 * q + 2 * i] = f16_lo_to_f32(hh[i]) + f16_lo_to_f32(ll[i]);
+                x[8 * q + 2 * i + 1] = f16_hi_to_f32(hh[i]) + f16_hi_to_f32(ll[i]);
+              }
             }
             store_tile_coalesced(tbuf, x, stash + (size_t)P * p.enc_cum[0] + (size_t)wrow0 * 64 + 32 * half, 64, lane,
                                  rows_valid);
@@ -536,8 +555,9 @@ mlp_chain_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ bl
           }
           ca.mword_in = mw[0];
           ca.mword_out = (kMode == 0 && mask_row && valid) ? mask_row + (c0a >> 5) : nullptr;
-          ca.tmem_hi = tmem + lane_base + kColAhi + c0a;
-          ca.tmem_lo = tmem + lane_base + kColAlo + c0a;
+          constexpr int kPack = kMode == 0 ? 2 : 1;  // forward: two fp16 per column
+          ca.tmem_hi = tmem + lane_base + kColAhi + c0a / kPack;
+          ca.tmem_lo = tmem + lane_base + kColAlo + c0a / kPack;
           epilogue_chunk_dispatch<kMode>(hsel >= 0, train, v0, c0a, ca, hacc);
           if (has_next) {
             tmem_wait_st();
@@ -547,8 +567,8 @@ mlp_chain_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ bl
           if (nch == 2) {
             ca.mword_in = mw[1];
             ca.mword_out = (kMode == 0 && mask_row && valid) ? mask_row + (c0b >> 5) : nullptr;
-            ca.tmem_hi = tmem + lane_base + kColAhi + c0b;
-            ca.tmem_lo = tmem + lane_base + kColAlo + c0b;
+            ca.tmem_hi = tmem + lane_base + kColAhi + c0b / kPack;
+            ca.tmem_lo = tmem + lane_base + kColAlo + c0b / kPack;
             epilogue_chunk_dispatch<kMode>(hsel >= 0, train, v1, c0b, ca, hacc);
           }
         }

@@ -9,6 +9,7 @@
 #include <math_constants.h>
 
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace nerfb200 {
 
@@ -220,20 +221,22 @@ __global__ void pack_kernel(Plan p, const float* __restrict__ flat, float* __res
         val = flat[g.flat_b + (idx - g.b_off)];
         found = true;
       } else if (idx >= g.tc_off && idx < g.tc_off + 2 * g.k_tc * g.n) {
-        // [kstep][hi|lo][slab 0|1][n][4]: element (n, k = kstep*8 + slab*4 + j)
+        // forward operand, fp16 x 2 split: [k-step of 16][hi|lo][slab 0|1][n][8 halves]; this float slot holds the
+        // halves of (n, k) and (n, k + 1) with k = kstep*16 + slab*8 + 2j (low half = k).  K is padded to a multiple
+        // of 16 with zeros; the region was sized for the tf32 copy (2 k_tc n floats), the tail stays zero.
         const int e = idx - g.tc_off;
         const int per_step = 16 * g.n;
         const int ks = e / per_step, r = e - ks * per_step;
         const int part = r / (8 * g.n), r2 = r - part * 8 * g.n;
         const int slab = r2 / (4 * g.n), r3 = r2 - slab * 4 * g.n;
         const int nn = r3 >> 2, j = r3 & 3;
-        const int k = ks * 8 + slab * 4 + j;
-        float w = 0.f;
-        if (k < g.k_h || k - g.k_h < g.enc_real) w = flat[g.flat_w + nn * in_real + k];
-        uint32_t hb;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(w));
-        const float hi = __uint_as_float(hb);
-        val = part == 0 ? hi : w - hi;
+        const int k = ks * 16 + slab * 8 + 2 * j;
+        float w0 = 0.f, w1 = 0.f;
+        if (k < g.k_tc && (k < g.k_h || k - g.k_h < g.enc_real)) w0 = flat[g.flat_w + nn * in_real + k];
+        if (k + 1 < g.k_tc && (k + 1 < g.k_h || k + 1 - g.k_h < g.enc_real)) w1 = flat[g.flat_w + nn * in_real + k + 1];
+        uint32_t hi, lo;
+        tc::split_f16x2(w0, w1, hi, lo);
+        val = __uint_as_float(part == 0 ? hi : lo);
         found = true;
       } else if (idx >= g.tcd_off && idx < g.tcd_off + 2 * g.k_h * g.n) {
         // dgrad operand: [kstep over n][hi|lo][slab 0|1][k < k_h][4]: element (k, n = kstep*8 + slab*4 + j) = W[n][k]

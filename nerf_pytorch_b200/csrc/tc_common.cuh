@@ -91,6 +91,42 @@ __device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a_tmem, uint64_t b, 
       "r"(a_tmem), "l"(b), "r"(idesc), "r"(acc)
       : "memory");
 }
+// fp16 operands (forward chain): D = F32, A = B = F16, both K-major, M = 128; K = 16 per instruction
+__device__ __forceinline__ uint32_t make_idesc_f16(int n) {
+  return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+}
+__device__ __forceinline__ void mma_ss_f16(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(d),
+      "l"(a), "l"(b), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void mma_ts_f16(uint32_t d, uint32_t a_tmem, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}\n" ::"r"(d),
+      "r"(a_tmem), "l"(b), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// fp16 x 2 split of a pair of fp32 values: hi = fp16(x) (saturating), lo = fp16(x - hi); both packed with the
+// FIRST value in the low half (= the lower K index of a 16-bit tensor-memory / shared-memory operand)
+__device__ __forceinline__ void split_f16x2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
+  float h0, h1;
+  asm("{\n.reg .b16 a, b;\nmov.b32 {a, b}, %2;\ncvt.f32.f16 %0, a;\ncvt.f32.f16 %1, b;\n}\n" : "=f"(h0), "=f"(h1) : "r"(hi));
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(x1 - h1), "f"(x0 - h0));
+}
+__device__ __forceinline__ float f16_lo_to_f32(uint32_t pair) {
+  float f;
+  asm("{\n.reg .b16 a, b;\nmov.b32 {a, b}, %1;\ncvt.f32.f16 %0, a;\n}\n" : "=f"(f) : "r"(pair));
+  return f;
+}
+__device__ __forceinline__ float f16_hi_to_f32(uint32_t pair) {
+  float f;
+  asm("{\n.reg .b16 a, b;\nmov.b32 {a, b}, %1;\ncvt.f32.f16 %0, b;\n}\n" : "=f"(f) : "r"(pair));
+  return f;
+}
 // one lane of a converged warp (the warp runs the surrounding loop uniformly so that descriptors and addresses
 // live in uniform registers; only the tcgen05 instruction itself is predicated on the elected lane)
 __device__ __forceinline__ bool elect_one() {
@@ -129,6 +165,13 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
       "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,"
       "%29,%30,%31};\n" ::NB_W32(v, 0),
       NB_W32(v, 8), NB_W32(v, 16), NB_W32(v, 24), "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%16], "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15};\n" ::NB_W32(v, 0),
+      NB_W32(v, 8), "r"(taddr)
       : "memory");
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }

@@ -5,11 +5,13 @@
 //     x * w  ~=  x_hi*w_hi + x_lo*w_hi + x_hi*w_lo
 // accumulated in fp32 in tensor memory (single-pass TF32/BF16 misses the 1e-4
 // bar on the shipped checkpoints; the 3-term split meets it).
-//   forward: fp16 x 2 split (x_hi = fp16(x), x_lo = fp16(x - x_hi): 22 significant bits, products exact in the fp32
-//            accumulator), tcgen05.mma.kind::f16 with K = 16 per instruction -- half the tensor time of tf32.
-//            Activations, encodings and weights of a NeRF sit far inside fp16's range (|v| < 65504, absolute
-//            resolution 3e-8 below 0.125); conversions saturate instead of producing infinities.
-//   dgrad  : 3xTF32 (x_hi = tf32(x), x_lo = x - x_hi): gradients span too many decades for fp16.
+// with an fp16 x 2 split of both operands (x_hi = fp16(x), x_lo = fp16((x - x_hi) 2^11): 22 significant bits, products
+// exact in the fp32 accumulators; hi*hi and the 2^11-scaled cross terms accumulate separately) and tcgen05.mma.kind::f16, K = 16 per instruction -- half the tensor time of a 3xTF32 split.
+//   forward: activations, encodings and weights of a NeRF sit far inside fp16's range (6e-8 < |v| < 65504);
+//            conversions saturate instead of producing infinities.
+//   dgrad  : gradients span many decades ACROSS points (a sample's compositing weight scales its whole row), so
+//            every row runs in its own power-of-two scale: d_raw[row] is scaled to max-abs in [1, 2) on load, the
+//            chain is linear in it, and the gradient stash receives the exactly unscaled fp32 values.
 //
 // Persistent kernels, one CTA per SM, 320 threads:
 //   warps 0-7  prologue/epilogue: thread (row = tid % 128, half = tid / 128) owns half of the columns of row
@@ -22,8 +24,8 @@
 //              A from tensor memory (hidden activations / gradients) or shared memory (encodings), B = pre-split
 //              weights from the shared-memory ring (four k-steps per stage).
 //   warp 9     weight producer: one cp.async.bulk per stage from the L2-resident blob, mbarrier complete_tx.
-// Tensor memory (512 columns): [0,128) accumulator, [128,256) A_hi, [256,384) A_lo (forward: 64 columns each,
-// two fp16 per column).
+// Tensor memory (512 columns): [0,128) accumulator of hi*hi, [384,512) accumulator of the cross terms (scaled by
+// 2^11, see tc_common.cuh split_f16x2), [128,192) A_hi, [256,320) A_lo (two fp16 per column).
 // The direction encoding enters layers_dir[0] through a per-ray fp32 bias computed on the CUDA cores (it is
 // constant along a ray: SURVEY.md section 7.3 item 5), so that layer contracts over K = 128 only.
 #include "common.cuh"
@@ -46,7 +48,7 @@ constexpr int kStageBytes = kStepsPerStage * 8192;
 constexpr int kSlabBytes = 2048;      // 128 rows x 16 B
 constexpr int kMaxRaysPerTile = 10;
 constexpr uint32_t kTmemCols = 512;
-constexpr uint32_t kColAcc = 0, kColAhi = 128, kColAlo = 256;
+constexpr uint32_t kColAcc = 0, kColAhi = 128, kColAlo = 256, kColAcc2 = 384;  // Acc2: cross terms, scaled 2^11
 
 // Shared memory map (bytes from the 1 KB-aligned base).  The hi parts of the encodings are an SS-mode A operand in
 // shared memory, their lo parts live in tensor memory (columns [384, 448)).  `stage` is the 64 KB stash staging tile:
@@ -124,6 +126,7 @@ struct ChunkArgs {
   uint32_t* mword_out;    // fwd train: where to store the mask word (or nullptr when the row is out of range)
   uint8_t* stg_row;       // train: this row inside the staging tile (row * n * 4 bytes in), or nullptr
   int row7;               // row & 7: the stash chunk swizzle of this row (common.cuh swz_col)
+  float unscale;          // dgrad: 2^-s of this row's power-of-two scale (applied to what goes to the gradient stash)
   uint32_t tmem_hi, tmem_lo;  // destination addresses (already offset to column c0)
   bool has_next;
 };
@@ -170,28 +173,20 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int c0, 
   }
   if (kMode == 0 && kTrain && a.mword_out) *a.mword_out = bits;
   if (kTrain && a.stg_row) {
+    const float u = kMode == 1 ? a.unscale : 1.f;
 #pragma unroll
     for (int q = 0; q < 8; ++q)
       *reinterpret_cast<float4*>(a.stg_row + ((((c0 >> 2) + q) ^ a.row7) << 4)) =
-          make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+          kMode == 1 ? make_float4(x[4 * q] * u, x[4 * q + 1] * u, x[4 * q + 2] * u, x[4 * q + 3] * u)
+                     : make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
   }
   if (a.has_next) {
-    if (kMode == 0) {  // fp16 x 2: two K-adjacent values per tensor-memory column
-      uint32_t hi[16], lo[16];
+    // fp16 x 2: two K-adjacent values per tensor-memory column
+    uint32_t hi[16], lo[16];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) split_f16x2(x[2 * j], x[2 * j + 1], hi[j], lo[j]);
-      tmem_st16(a.tmem_hi, hi);
-      tmem_st16(a.tmem_lo, lo);
-    } else {
-      uint32_t hi[32], lo[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        hi[j] = tf32_hi(x[j]);
-        lo[j] = __float_as_uint(x[j] - __uint_as_float(hi[j]));
-      }
-      tmem_st32(a.tmem_hi, hi);
-      tmem_st32(a.tmem_lo, lo);
-    }
+    for (int j = 0; j < 16; ++j) split_f16x2(x[2 * j], x[2 * j + 1], hi[j], lo[j]);
+    tmem_st16(a.tmem_hi, hi);
+    tmem_st16(a.tmem_lo, lo);
   }
 }
 
@@ -287,7 +282,7 @@ mlp_chain_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ bl
           const GemmLayer& g = p.g[s];
           const uint32_t kbytes = kMode == 0 ? 64u * g.n : 64u * g.k_h;  // one k-step (hi + lo)
           const uint8_t* src = reinterpret_cast<const uint8_t*>(blob + (kMode == 0 ? g.tc_off : g.tcd_off));
-          const int ksteps = kMode == 0 ? (g.k_tc + 15) >> 4 : g.n >> 3;  // forward: fp16, K = 16 per step
+          const int ksteps = kMode == 0 ? (g.k_tc + 15) >> 4 : g.n >> 4;  // fp16: K = 16 per step
           for (int ks = 0; ks < ksteps; ks += kStepsPerStage) {
             const uint32_t bytes = (uint32_t)min(kStepsPerStage, ksteps - ks) * kbytes;
             mbar_wait(&bar_empty[pp.stage], pp.phase ^ 1);
@@ -316,11 +311,11 @@ mlp_chain_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ bl
           if (s < 0) continue;
           const GemmLayer& g = p.g[s];
           const int n_mma = kMode == 0 ? g.n : g.k_h;
-          const uint32_t idesc = kMode == 0 ? make_idesc_f16(n_mma) : make_idesc(n_mma);
+          const uint32_t idesc = make_idesc_f16(n_mma);
           const uint32_t slab_b = 16u * n_mma;  // bytes of one weight slab
-          const int ksteps = kMode == 0 ? (g.k_tc + 15) >> 4 : g.n >> 3;
+          const int ksteps = kMode == 0 ? (g.k_tc + 15) >> 4 : g.n >> 4;
           const int ksteps_h = kMode == 0 ? (g.k_h >> 4) : ksteps;  // k-steps whose A operand is in tensor memory
-          constexpr int kHalfSteps = kMode == 0 ? 4 : 8;            // k-steps covered by A columns [0, 64)
+          constexpr int kHalfSteps = 4;                             // k-steps covered by A columns [0, 64)
           mbar_wait(bar_a1, a_phase);
           tc_fence_after();
           bool second = false;  // bar_a2 of this layer consumed?
@@ -343,21 +338,17 @@ mlp_chain_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ bl
                 const uint64_t b_lo = make_desc(wb + 2 * slab_b, slab_b, 128);
                 const uint32_t acc0 = ks > 0 ? 1u : 0u;
                 const uint32_t a_hi = tmem + kColAhi + 8 * ks, a_lo = tmem + kColAlo + 8 * ks;
-                if (kMode == 1) {
-                  mma_ts(tmem + kColAcc, a_hi, b_hi, idesc, acc0);
-                  mma_ts(tmem + kColAcc, a_lo, b_hi, idesc, 1u);
-                  mma_ts(tmem + kColAcc, a_hi, b_lo, idesc, 1u);
-                } else if (ks < ksteps_h) {
+                if (ks < ksteps_h) {
                   mma_ts_f16(tmem + kColAcc, a_hi, b_hi, idesc, acc0);
-                  mma_ts_f16(tmem + kColAcc, a_lo, b_hi, idesc, 1u);
-                  mma_ts_f16(tmem + kColAcc, a_hi, b_lo, idesc, 1u);
+                  mma_ts_f16(tmem + kColAcc2, a_lo, b_hi, idesc, acc0);
+                  mma_ts_f16(tmem + kColAcc2, a_hi, b_lo, idesc, 1u);
                 } else {  // encodings: both halves are shared-memory operands (8 slabs hi, 8 slabs lo)
                   const uint32_t off = (uint32_t)(ks - ksteps_h) * 2 * kSlabBytes;
                   const uint64_t e_hi_d = make_desc(e_hi + off, kSlabBytes, 128);
                   const uint64_t e_lo_d = make_desc(e_hi + 8 * kSlabBytes + off, kSlabBytes, 128);
                   mma_ss_f16(tmem + kColAcc, e_hi_d, b_hi, idesc, acc0);
-                  mma_ss_f16(tmem + kColAcc, e_lo_d, b_hi, idesc, 1u);
-                  mma_ss_f16(tmem + kColAcc, e_hi_d, b_lo, idesc, 1u);
+                  mma_ss_f16(tmem + kColAcc2, e_lo_d, b_hi, idesc, acc0);
+                  mma_ss_f16(tmem + kColAcc2, e_hi_d, b_lo, idesc, 1u);
                 }
               }
             }
@@ -392,6 +383,7 @@ mlp_chain_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ bl
       const int rows_valid = (int)(P - wrow0 < 32 ? (P - wrow0 < 0 ? 0 : P - wrow0) : 32);
       int ray_slot = 0;
       float dr[4] = {0.f, 0.f, 0.f, 0.f};
+      float row_unscale = 1.f;
 
       if (kMode == 0) {
         const int64_t ray = pt / S;
@@ -466,8 +458,8 @@ mlp_chain_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ bl
               const uint32_t hh[4] = {h8.x, h8.y, h8.z, h8.w}, ll[4] = {l8.x, l8.y, l8.z, l8.w};
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
-                x[8 * q + 2 * i] = f16_lo_to_f32(hh[i]) + f16_lo_to_f32(ll[i]);
-                x[8 * q + 2 * i + 1] = f16_hi_to_f32(hh[i]) + f16_hi_to_f32(ll[i]);
+                x[8 * q + 2 * i] = fmaf(f16_lo_to_f32(ll[i]), kLoInv, f16_lo_to_f32(hh[i]));
+                x[8 * q + 2 * i + 1] = fmaf(f16_hi_to_f32(ll[i]), kLoInv, f16_hi_to_f32(hh[i]));
               }
             }
             store_tile_coalesced(tbuf, x, stash + (size_t)P * p.enc_cum[0] + (size_t)wrow0 * 64 + 32 * half, 64, lane,
@@ -483,7 +475,13 @@ mlp_chain_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ bl
         mbar_arrive(bar_a2);
       } else {
         const float4 d4 = valid ? reinterpret_cast<const float4*>(raw)[pt] : make_float4(0.f, 0.f, 0.f, 0.f);
-        dr[0] = d4.x; dr[1] = d4.y; dr[2] = d4.z; dr[3] = d4.w;
+        // this row's power-of-two scale: 2^(127 - e) with e the biased exponent of max |d_raw[row]| (1 for zero rows)
+        const float m = fmaxf(fmaxf(fabsf(d4.x), fabsf(d4.y)), fmaxf(fabsf(d4.z), fabsf(d4.w)));
+        const uint32_t e = (__float_as_uint(m) >> 23) & 0xFFu;
+        const bool scaled = e >= 1u && e <= 253u;
+        const float sc = scaled ? __uint_as_float((254u - e) << 23) : 1.f;
+        row_unscale = scaled ? __uint_as_float(e << 23) : 1.f;
+        dr[0] = d4.x * sc; dr[1] = d4.y * sc; dr[2] = d4.z * sc; dr[3] = d4.w * sc;
       }
       t_pro += clock64() - t0;
 
@@ -538,6 +536,7 @@ mlp_chain_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ bl
           ca.dr[0] = dr[0]; ca.dr[1] = dr[1]; ca.dr[2] = dr[2]; ca.dr[3] = dr[3];
           ca.has_next = has_next;
           ca.row7 = row & 7;
+          ca.unscale = row_unscale;
           ca.stg_row = train ? staging + (size_t)row * g.n * 4 : nullptr;
           // column chunks of this thread: first [32*half, +32), second [64 + 32*half, +32) (128-wide layers only).
           // Both are pulled out of the accumulator up front; after the first chunk's A columns are stored the
@@ -546,16 +545,29 @@ mlp_chain_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ bl
           const int c0a = 32 * half, c0b = 64 + 32 * half;
           uint32_t v0[32], v1[32];
           if (has_mma) {
+            // hi*hi accumulator + 2^-11 x cross-term accumulator of the same columns (16 at a time: registers)
+            auto fold = [&](uint32_t (&v)[32], int c0) {
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                uint32_t w[16];
+                tmem_ld16(tmem + lane_base + kColAcc2 + c0 + 16 * h, w);
+                tmem_wait_ld();
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                  v[16 * h + j] = __float_as_uint(fmaf(__uint_as_float(w[j]), kLoInv, __uint_as_float(v[16 * h + j])));
+              }
+            };
             tmem_ld32(tmem + lane_base + kColAcc + c0a, v0);
             if (nch == 2) tmem_ld32(tmem + lane_base + kColAcc + c0b, v1);
-            tmem_wait_ld();
+            fold(v0, c0a);
+            if (nch == 2) fold(v1, c0b);
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v0[j] = v1[j] = 0u;
           }
           ca.mword_in = mw[0];
           ca.mword_out = (kMode == 0 && mask_row && valid) ? mask_row + (c0a >> 5) : nullptr;
-          constexpr int kPack = kMode == 0 ? 2 : 1;  // forward: two fp16 per column
+          constexpr int kPack = 2;  // two fp16 per tensor-memory column
           ca.tmem_hi = tmem + lane_base + kColAhi + c0a / kPack;
           ca.tmem_lo = tmem + lane_base + kColAlo + c0a / kPack;
           epilogue_chunk_dispatch<kMode>(hsel >= 0, train, v0, c0a, ca, hacc);

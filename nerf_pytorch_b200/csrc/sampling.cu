@@ -239,19 +239,20 @@ __global__ void pack_kernel(Plan p, const float* __restrict__ flat, float* __res
         val = __uint_as_float(part == 0 ? hi : lo);
         found = true;
       } else if (idx >= g.tcd_off && idx < g.tcd_off + 2 * g.k_h * g.n) {
-        // dgrad operand: [kstep over n][hi|lo][slab 0|1][k < k_h][4]: element (k, n = kstep*8 + slab*4 + j) = W[n][k]
+        // dgrad operand, fp16 x 2 split: [k-step of 16 over n][hi|lo][slab 0|1][k < k_h][8 halves]; this float slot
+        // holds W[n][k] and W[n + 1][k] with n = kstep*16 + slab*8 + 2j (the tail of the region stays zero)
         const int e = idx - g.tcd_off;
         const int per_step = 16 * g.k_h;
         const int ks = e / per_step, r = e - ks * per_step;
         const int part = r / (8 * g.k_h), r2 = r - part * 8 * g.k_h;
         const int slab = r2 / (4 * g.k_h), r3 = r2 - slab * 4 * g.k_h;
         const int k = r3 >> 2, j = r3 & 3;
-        const int nn = ks * 8 + slab * 4 + j;
-        const float w = flat[g.flat_w + nn * in_real + k];
-        uint32_t hb;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(w));
-        const float hi = __uint_as_float(hb);
-        val = part == 0 ? hi : w - hi;
+        const int nn = ks * 16 + slab * 8 + 2 * j;
+        const float w0 = nn < g.n ? flat[g.flat_w + nn * in_real + k] : 0.f;
+        const float w1 = nn + 1 < g.n ? flat[g.flat_w + (nn + 1) * in_real + k] : 0.f;
+        uint32_t hi, lo;
+        tc::split_f16x2(w0, w1, hi, lo);
+        val = __uint_as_float(part == 0 ? hi : lo);
         found = true;
       }
     }

@@ -109,13 +109,18 @@ __device__ __forceinline__ void mma_ts_f16(uint32_t d, uint32_t a_tmem, uint64_t
       "r"(a_tmem), "l"(b), "r"(idesc), "r"(acc)
       : "memory");
 }
-// fp16 x 2 split of a pair of fp32 values: hi = fp16(x) (saturating), lo = fp16(x - hi); both packed with the
-// FIRST value in the low half (= the lower K index of a 16-bit tensor-memory / shared-memory operand)
+// fp16 x 2 split of a pair of fp32 values: hi = fp16(x) (saturating), lo = fp16((x - hi) * 2^11); both packed with
+// the FIRST value in the low half (= the lower K index of a 16-bit tensor-memory / shared-memory operand).
+// The residual is scaled by 2^11 so that it is a NORMAL fp16 number whenever hi is (it would be subnormal below
+// |x| = 0.125 otherwise and the split would degrade to 3e-8 absolute resolution): x = hi + lo * 2^-11 carries 22
+// significant bits for 6e-8 < |x| < 65504.  The cross terms hi*lo and lo*hi therefore accumulate into a second
+// accumulator that the epilogue folds in with the factor 2^-11.
+constexpr float kLoScale = 2048.f, kLoInv = 1.f / 2048.f;
 __device__ __forceinline__ void split_f16x2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
   asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
   float h0, h1;
   asm("{\n.reg .b16 a, b;\nmov.b32 {a, b}, %2;\ncvt.f32.f16 %0, a;\ncvt.f32.f16 %1, b;\n}\n" : "=f"(h0), "=f"(h1) : "r"(hi));
-  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(x1 - h1), "f"(x0 - h0));
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"((x1 - h1) * kLoScale), "f"((x0 - h0) * kLoScale));
 }
 __device__ __forceinline__ float f16_lo_to_f32(uint32_t pair) {
   float f;
@@ -165,6 +170,13 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
       "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,"
       "%29,%30,%31};\n" ::NB_W32(v, 0),
       NB_W32(v, 8), NB_W32(v, 16), NB_W32(v, 24), "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+      : NB_R32(v, 0), NB_R32(v, 8)
+      : "r"(taddr)
       : "memory");
 }
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {

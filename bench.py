@@ -374,7 +374,10 @@ def run_ours(args):
             "e2e": {"value": RAYS_PER_GPU * world / (e2e_ms / 1e3), "unit": "rays/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": 3 * RAYS_PER_GPU * 3 * 4, "d2h_bytes_per_step": 4},
             "fwd_only": {"value": RAYS_PER_GPU * world / (fwd_ms / 1e3), "unit": "rays/s", "ms_per_step": fwd_ms},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "roofline_bwd": roof_bwd,
+            "gpu_launches": int(launches), "clocks": clocks,
+            # `roofline` = the kernel with the largest share of the step (profiles/r1_final_tc_A1_launch_shares.csv:
+            # wgrad 38 %, dgrad chain 31 %, forward chain 29 %): HBM-bound; the two tensor-bound chain kernels follow
+            "roofline": (roof_bwd or {}).get("wgrad") or roof, "roofline_fwd": roof, "roofline_bwd": roof_bwd,
             "cpu_baseline": cpu,
         }
         print(json.dumps(line))

@@ -31,12 +31,13 @@ struct GemmLayer {
   int flat_b;    // offset of bias[n] in the flat vector
   int src;       // gemm index whose output is this layer's h-input (-1 for layer1)
   // tcgen05 operand copy (mlp_tc.cu): k_tc = K the tensor-core path contracts over (the direction
-  // encoding of layers_dir[0] is hoisted out per ray, so k_tc = k_h there); per k-step of 8 the blob
-  // holds [hi slab0 | hi slab1 | lo slab0 | lo slab1], slab = [n][4 floats] (UMMA canonical K-major,
-  // no swizzle: 8-row core matrices 128 B apart, the two K halves one slab apart).
+  // encoding of layers_dir[0] is hoisted out per ray, so k_tc = k_h there); per k-step of 16 the blob
+  // holds [hi slab0 | hi slab1 | lo slab0 | lo slab1], slab = [n][8 fp16] (UMMA canonical K-major,
+  // no swizzle: 8-row core matrices 128 B apart, the two K halves one slab apart); fp16 x 2 split with a
+  // 2^11-scaled residual (tc_common.cuh split_f16x2).
   int k_tc;
   int tc_off;
-  // dgrad operand copy: Wt[k < k_h][n] as K-major slabs over the reduction index n, hi|lo per 8 n
+  // dgrad operand copy: Wt[k < k_h][n] as K-major slabs over the reduction index n, hi|lo per 16 n
   int tcd_off;
   int mask_cum;  // ReLU bit-mask words (uint32, one bit per output) per point before this layer's
 };

@@ -17,10 +17,10 @@
 //   warps 0-7  prologue/epilogue: thread (row = tid % 128, half = tid / 128) owns half of the columns of row
 //              `row` of the 128-point tile (= TMEM lane row).  Per layer: tcgen05.ld the fp32 accumulator,
 //              + bias / ReLU (forward) or + head term / ReLU mask (dgrad), narrow heads as register dot
-//              products, split into tf32 hi + lo and tcgen05.st back into tensor memory as the NEXT layer's A
+//              products, split into fp16 hi + lo and tcgen05.st back into tensor memory as the NEXT layer's A
 //              operand; training outputs (activation stash, ReLU bit mask, gradient stash) leave through a
 //              per-warp swizzled shared-memory transpose so that every global store is a full 128-byte row.
-//   warp 8     MMA issuer: one elected lane, tcgen05.mma M=128, N=128|64, K=16 (f16) | 8 (tf32), three per k-step;
+//   warp 8     MMA issuer: one elected lane, tcgen05.mma.kind::f16 M=128, N=128|64, K=16, three per k-step;
 //              A from tensor memory (hidden activations / gradients) or shared memory (encodings), B = pre-split
 //              weights from the shared-memory ring (four k-steps per stage).
 //   warp 9     weight producer: one cp.async.bulk per stage from the L2-resident blob, mbarrier complete_tx.
@@ -115,7 +115,7 @@ __device__ __forceinline__ int consumer_of(const Plan& p, int t) {
 //   forward: y = max(acc + bias, lb)                      (lb = 0 with ReLU, -inf without; bias already holds the
 //                                                           per-ray direction term for layers_dir[0])
 //   dgrad  : y = (acc + sum_c d_raw[c] * W_head[c]) masked by the forward ReLU bit
-// then y -> tf32 hi / lo -> tensor memory (next layer's A operand).
+// then y -> fp16 hi / lo -> tensor memory (next layer's A operand).
 struct ChunkArgs {
   const float* bias;      // fwd: 128 floats for this layer (per-thread pointer)
   float lb;               // fwd: ReLU lower bound

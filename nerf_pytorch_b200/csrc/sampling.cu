@@ -223,7 +223,7 @@ __global__ void pack_kernel(Plan p, const float* __restrict__ flat, float* __res
       } else if (idx >= g.tc_off && idx < g.tc_off + 2 * g.k_tc * g.n) {
         // forward operand, fp16 x 2 split: [k-step of 16][hi|lo][slab 0|1][n][8 halves]; this float slot holds the
         // halves of (n, k) and (n, k + 1) with k = kstep*16 + slab*8 + 2j (low half = k).  K is padded to a multiple
-        // of 16 with zeros; the region was sized for the tf32 copy (2 k_tc n floats), the tail stays zero.
+        // of 16 with zeros; the region is 2 k_tc n floats, its tail stays zero.
         const int e = idx - g.tc_off;
         const int per_step = 16 * g.n;
         const int ks = e / per_step, r = e - ks * per_step;

@@ -15,7 +15,7 @@ from . import _lib
 from ._lib import Arch, RenderOpts
 
 IMPL_SIMT = 0  # fp32 CUDA cores
-IMPL_TC = 1    # tcgen05 tensor cores (3xTF32)
+IMPL_TC = 1    # tcgen05 tensor cores (fp16x2 / 3xTF32 three-term splits, fp32 accumulation)
 
 
 def _ptr(t: Optional[torch.Tensor]):

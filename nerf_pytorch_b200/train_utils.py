@@ -26,7 +26,7 @@ from .nerf_helpers import Embedder, get_minibatches, ndc_rays
 # so validation renders use options.nerf.train.* for sampling/noise.  True reproduces that.
 COMPAT_MODE_QUIRK = True
 
-# None: tcgen05 tensor cores (3xTF32) wherever the kernels support the configuration (hidden 128, encodings
+# None: tcgen05 tensor cores (three-term split-precision products) wherever the kernels support the configuration (hidden 128, encodings
 # <= 64 wide, >= 16 samples per ray), fp32 CUDA cores otherwise; 0 / 1 force one implementation.
 DEFAULT_IMPL = None
 

@@ -1,6 +1,6 @@
 """GPU: BASELINE.json's full-size configurations through size-independent properties (the oracle is too slow at
 these sizes): sortedness / containment of the merged depths, compositing invariants, bit-determinism, ray-chunk
-invariance, agreement of the two kernel families (fp32 CUDA cores vs tcgen05 3xTF32) forward and backward."""
+invariance, agreement of the two kernel families (fp32 CUDA cores vs tcgen05 split precision) forward and backward."""
 import math
 
 import pytest

@@ -1,7 +1,8 @@
-"""GPU: the tcgen05 (3xTF32) forward against the fp32 CUDA-core kernel and the oracle.
+"""GPU: the tcgen05 kernels against the fp32 CUDA-core kernels and the oracle.
 
-3xTF32 keeps ~21 bits of every product (x_hi*w_hi + x_lo*w_hi + x_hi*w_lo, fp32 accumulate), so the bar is
-the same as for the fp32 path: relative 1e-4 of the output scale, per north_star."""
+The three-term splits (fp16x2 with a scaled residual in the chain kernels, 3xTF32 in wgrad) keep ~21 bits of every
+product (x_hi*w_hi + x_lo*w_hi + x_hi*w_lo, fp32 accumulate), so the bar is the same as for the fp32 path:
+relative 1e-4 of the output scale, per north_star."""
 import pytest
 import torch
 

@@ -112,8 +112,8 @@ int32_t nerfb200_encode(const nerfb200_arch_t* arch, int32_t which, const float*
  * post-activation output of every hidden linear (needed by the backward entry points).
  * impl: 0 = fp32 CUDA cores (bit-faithful fp32 FMA), 1 = tcgen05 tensor cores: every product as a three-term
  * split (fp16 x 2 operands with a 2^11-scaled residual, fp32 accumulation; ~22 significant bits per operand).
- * The split represents magnitudes in 6e-8 .. 65504; larger activations / weights saturate (a NeRF's stay far
- * inside; use impl 0 for networks that do not). */
+ * The split carries 22 bits for magnitudes in 6.1e-5 .. 65504 and resolves 1.5e-11 absolutely below; larger
+ * activations / weights saturate (a NeRF's stay far inside; use impl 0 for networks that do not). */
 int64_t nerfb200_stash_floats(const nerfb200_arch_t* arch, int64_t n_points);
 int32_t nerfb200_mlp_fwd(const nerfb200_arch_t* arch, const float* blob, const float* rays, int32_t ray_stride,
                          const float* z, int64_t n_rays, int32_t n_samples, float* raw, float* stash,

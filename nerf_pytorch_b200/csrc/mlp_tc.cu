@@ -7,7 +7,7 @@
 // bar on the shipped checkpoints; the 3-term split meets it).
 // with an fp16 x 2 split of both operands (x_hi = fp16(x), x_lo = fp16((x - x_hi) 2^11): 22 significant bits, products
 // exact in the fp32 accumulators; hi*hi and the 2^11-scaled cross terms accumulate separately) and tcgen05.mma.kind::f16, K = 16 per instruction -- half the tensor time of a 3xTF32 split.
-//   forward: activations, encodings and weights of a NeRF sit far inside fp16's range (6e-8 < |v| < 65504);
+//   forward: activations, encodings and weights of a NeRF sit far inside the split's range (|v| < 65504);
 //            conversions saturate instead of producing infinities.
 //   dgrad  : gradients span many decades ACROSS points (a sample's compositing weight scales its whole row), so
 //            every row runs in its own power-of-two scale: d_raw[row] is scaled to max-abs in [1, 2) on load, the

@@ -113,7 +113,7 @@ __device__ __forceinline__ void mma_ts_f16(uint32_t d, uint32_t a_tmem, uint64_t
 // the FIRST value in the low half (= the lower K index of a 16-bit tensor-memory / shared-memory operand).
 // The residual is scaled by 2^11 so that it is a NORMAL fp16 number whenever hi is (it would be subnormal below
 // |x| = 0.125 otherwise and the split would degrade to 3e-8 absolute resolution): x = hi + lo * 2^-11 carries 22
-// significant bits for 6e-8 < |x| < 65504.  The cross terms hi*lo and lo*hi therefore accumulate into a second
+// significant bits for 6.1e-5 <= |x| < 65504 and resolves 1.5e-11 absolutely below (tests/test_host_cpu.py).  The cross terms hi*lo and lo*hi therefore accumulate into a second
 // accumulator that the epilogue folds in with the factor 2^-11.
 constexpr float kLoScale = 2048.f, kLoInv = 1.f / 2048.f;
 __device__ __forceinline__ void split_f16x2(float x0, float x1, uint32_t& hi, uint32_t& lo) {

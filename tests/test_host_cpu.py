@@ -2,6 +2,7 @@
 its host-side planning functions answer correctly, and the Python host logic (encoder probing,
 model introspection, sharding) behaves.  No compute kernels are launched here."""
 import ctypes as C
+import math
 import os
 import re
 
@@ -116,3 +117,53 @@ def test_shard_bounds_partition():
         assert spans[0][0] == 0 and spans[-1][1] == n
         assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
         assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+
+
+def test_fp16x2_split_precision_model():
+    """CPU model of the operand split the tcgen05 chain kernels use (csrc/tc_common.cuh split_f16x2):
+    hi = fp16(x) saturating, lo = fp16((x - hi) * 2^11); x ~= hi + lo * 2^-11.  Pins the documented claims: ~22
+    significant bits over 6.1e-5 <= |x| < 65504 (1.5e-11 absolute below), and a three-term product sum (hi*hi + 2^-11 (lo*hi + hi*lo), fp32
+    accumulation) that stays far inside the 1e-4 parity bar where a plain fp16 or tf32 product does not."""
+    import torch
+
+    def split(x):
+        hi = x.clamp(-65504.0, 65504.0).to(torch.float16)
+        lo = ((x - hi.float()) * 2048.0).clamp(-65504.0, 65504.0).to(torch.float16)
+        return hi.float(), lo.float()
+
+    g = torch.Generator().manual_seed(0)
+    # magnitudes log-uniform over the claimed range, both signs
+    mag = torch.exp(torch.empty(200000).uniform_(math.log(1e-7), math.log(6e4), generator=g))
+    x = mag * torch.where(torch.rand(200000, generator=g) < 0.5, -1.0, 1.0)
+    hi, lo = split(x)
+    err = ((hi.double() + lo.double() / 2048.0) - x.double()).abs()
+    normal = x.abs() >= 6.2e-5  # hi is a normal fp16 number
+    assert (err[normal] / x.double().abs()[normal]).max().item() < 2.0 ** -20
+    assert err[~normal].max().item() < 2e-11
+    # the unscaled residual would be subnormal below 0.125 and lose that precision
+    lo_plain = (x - hi).to(torch.float16).float()
+    small = x.abs() < 1e-3
+    rel_plain = ((hi.double() + lo_plain.double()) - x.double()).abs() / x.double().abs()
+    assert rel_plain[small].max().item() > 2.0 ** -16
+
+    # a 128-wide layer: activations ~ ReLU outputs, weights ~ trained-NeRF scale
+    a = torch.randn(512, 128, generator=g).clamp_min(0) * 3.0
+    w = torch.randn(128, 128, generator=g) * 0.2
+    ref = a.double() @ w.double().t()
+    ah, al = split(a)
+    wh, wl = split(w)
+    got = ah @ wh.t() + (al @ wh.t() + ah @ wl.t()) / 2048.0
+    scale = ref.abs().max().item()
+    assert (got.double() - ref).abs().max().item() <= 2e-6 * scale
+    single = a.to(torch.float16).float() @ w.to(torch.float16).float().t()
+    assert (single.double() - ref).abs().max().item() > 1e-4 * scale  # why one fp16 term is not enough
+
+    # dgrad rows run in their own power-of-two scale: max-abs of the row lands in [1, 2), exactly invertible
+    d = torch.randn(1000, 4, generator=g) * torch.exp(torch.empty(1000, 1).uniform_(-40, 10, generator=g))
+    m = d.abs().amax(dim=1)
+    e = (m.view(torch.int32) >> 23) & 0xFF
+    sc = ((254 - e) << 23).view(torch.float32)
+    scaled = d * sc[:, None]
+    smax = scaled.abs().amax(dim=1)
+    assert bool(((smax >= 1.0) & (smax < 2.0)).all())
+    assert torch.equal(scaled * (e << 23).view(torch.float32)[:, None], d)

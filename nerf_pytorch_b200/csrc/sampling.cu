@@ -94,9 +94,12 @@ sample_pdf_merge_kernel(const float* __restrict__ z_coarse, const float* __restr
   if (r >= n_rays) return;  // whole warp exits together; only __syncwarp below
   const int nb = nc - 1;    // bins = mid-points = cdf entries
   const int nw = nc - 2;    // interior weights
-  float* sort = smem + (size_t)warp * (npow2 + 2 * nc);
+  // per-warp buffers: sort[npow2] | cdf[nc] | bins[nc] | pdf[nc]  (pdf has its own region: npow2 can be smaller
+  // than nc + (nc - 2) when n_fine < n_coarse - 2, so it must not live inside the sort buffer)
+  float* sort = smem + (size_t)warp * (npow2 + 3 * nc);
   float* cdf = sort + npow2;
   float* bins = cdf + nc;
+  float* pdf = bins + nc;
 
   const float* zc = z_coarse + r * nc;
   for (int i = lane; i < nc; i += 32) sort[i] = zc[i];
@@ -115,7 +118,6 @@ sample_pdf_merge_kernel(const float* __restrict__ z_coarse, const float* __restr
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
     const float total = (float)part;
-    float* pdf = sort + nc;  // scratch inside the sort buffer (npow2 >= nc + nf >= nc + nw)
     for (int j = lane; j < nw; j += 32) pdf[j] = __fdiv_rn(__fadd_rn(w[j], 1e-5f), total);
     __syncwarp();
     if (lane == 0) {
@@ -180,7 +182,7 @@ int launch_sample_pdf_merge(const float* z_coarse, const float* weights_coarse, 
                             float* z_samples, int32_t* inds, float* cdf_out, cudaStream_t s) {
   int npow2 = 1;
   while (npow2 < n_coarse + n_fine) npow2 <<= 1;
-  const size_t smem = (size_t)kPdfWarps * (npow2 + 2 * n_coarse) * sizeof(float);
+  const size_t smem = (size_t)kPdfWarps * (npow2 + 3 * n_coarse) * sizeof(float);
   if (smem > 48 * 1024) {
     int rc = check_cuda(cudaFuncSetAttribute(sample_pdf_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)smem),

@@ -330,20 +330,15 @@ def run_ours(args):
             achb = 2 * flops_fwd / (tb * 1e-3) / 1e12
             roof_bwd = {"kernel": "mlp_bwd (dgrad + wgrad kernels, fine pass)", "bound": "tensor", "achieved": achb,
                         "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achb / peaks["bf16_tflops"], "ms": tb}
-            # the two backward kernels apart (debug flags: 8 = no wgrad launch, 4 = no dgrad launch; the wgrad kernel
-            # then consumes the gradient stash the full calls above left in the workspace)
-            import ctypes
-            from nerf_pytorch_b200 import _lib
-            lib = _lib.load()
-            lib.nerfb200_debug_tc_flags(8)
-            t_dg = t_alone(lambda: ops.mlp_bwd(arch, blob, rays, z, G, stash, impl=impl))
-            lib.nerfb200_debug_tc_flags(4)
-            t_wg = t_alone(lambda: ops.mlp_bwd(arch, blob, rays, z, G, stash, impl=impl))
-            lib.nerfb200_debug_tc_flags(0)
+            # the two backward kernels apart (stage-level entry points of the C ABI)
+            gst = ops.mlp_dgrad(arch, blob, G, stash, impl=impl)
+            fg = torch.zeros(arch.flat_param_count(), dtype=torch.float32, device=dev)
+            t_dg = t_alone(lambda: ops.mlp_dgrad(arch, blob, G, stash, impl=impl, gstash=gst))
+            t_wg = t_alone(lambda: ops.mlp_wgrad(arch, rays, z, G, stash, gst, impl=impl, flat_grad=fg))
             roof_bwd["dgrad_ms"] = t_dg
             roof_bwd["wgrad_ms"] = t_wg
             if args.kernels == "tc" and impl == 1:
-                bpp = lib.nerfb200_debug_wgrad_bytes_per_point(ctypes.byref(arch.c_struct()))
+                bpp = ops.wgrad_bytes_per_point(arch)
                 wbytes = float(bpp) * RAYS_PER_GPU * (NC + NF)
                 tr = None
                 if os.path.exists(summ):
@@ -353,7 +348,7 @@ def run_ours(args):
                                      "peak_source": f"{peak_kind} copy bandwidth", "unit": "GB/s",
                                      "frac": wbytes / (t_wg * 1e-3) / 1e9 / peaks["hbm_gbs"],
                                      "algorithmic_bytes": wbytes, "traffic": tr, "ms": t_wg}
-            del stash, raw, G
+            del stash, raw, G, gst, fg
 
     # ---- CPU baseline beside it (rank 0, N = 1 only): bounded sample of the same step ----
     cpu = None

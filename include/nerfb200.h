@@ -65,16 +65,8 @@ int32_t nerfb200_version(void);
 const char* nerfb200_last_error(void);
 /* number of CUDA kernels this library has launched in this process (all threads) */
 int64_t nerfb200_launch_count(void);
-/* debug hook: device buffer of 8 int64 per CTA receiving the tcgen05 forward kernel's cycle counters
- * [prologue, wait-for-MMA, epilogue, total, tmem-load, chunk math+stores, tmem-store wait, head] of its
- * epilogue thread 0; NULL switches it off. */
-void nerfb200_debug_tc_profile(void* buf);
-/* debug hook for timing experiments: bit 0 skips the weight copies, bit 1 the MMAs (results are garbage);
- * bit 2 makes mlp_bwd skip its dgrad launch, bit 3 its wgrad launch (to time the two kernels apart: with bit 2 set
- * the wgrad kernel consumes the gradient stash a previous full call left in the workspace) */
-void nerfb200_debug_tc_flags(int32_t flags);
 /* HBM bytes the tcgen05 wgrad kernel reads per point: sum over its work items of one dY row + one X row */
-int64_t nerfb200_debug_wgrad_bytes_per_point(const nerfb200_arch_t* arch);
+int64_t nerfb200_wgrad_bytes_per_point(const nerfb200_arch_t* arch);
 
 /* ---- parameters -------------------------------------------------------------------------------
  * Canonical order of the linears ("slots"): layer1, layers_xyz[0..num_layers-2], then
@@ -151,6 +143,14 @@ int32_t nerfb200_sample_pdf_merge(const float* z_coarse, const float* weights_co
 int32_t nerfb200_mlp_bwd(const nerfb200_arch_t* arch, const float* blob, const float* rays, int32_t ray_stride,
                          const float* z, int64_t n_rays, int32_t n_samples, const float* d_raw,
                          const float* stash, float* gstash, float* flat_grad, int32_t impl, void* stream);
+/* The two halves of nerfb200_mlp_bwd as separate calls (autograd's accumulation of nn.Linear backward,
+ * nerf/models.py:233-256 replayed in reverse): dgrad walks the chain backwards and fills `gstash` with the
+ * pre-activation gradients; wgrad reduces dW = dY^T X over all points into `flat_grad` (+=). */
+int32_t nerfb200_mlp_dgrad(const nerfb200_arch_t* arch, const float* blob, const float* d_raw, const float* stash,
+                           float* gstash, int64_t n_points, int32_t impl, void* stream);
+int32_t nerfb200_mlp_wgrad(const nerfb200_arch_t* arch, const float* rays, int32_t ray_stride, const float* z,
+                           int64_t n_rays, int32_t n_samples, const float* d_raw, const float* stash,
+                           const float* gstash, float* flat_grad, int32_t impl, void* stream);
 
 /* ---- whole-path entry points ------------------------------------------------------------------- */
 

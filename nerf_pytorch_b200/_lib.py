@@ -55,9 +55,7 @@ SIGNATURES = {
     "nerfb200_version": (I32, []),
     "nerfb200_last_error": (C.c_char_p, []),
     "nerfb200_launch_count": (I64, []),
-    "nerfb200_debug_tc_profile": (None, [P]),
-    "nerfb200_debug_tc_flags": (None, [I32]),
-    "nerfb200_debug_wgrad_bytes_per_point": (I64, [P]),
+    "nerfb200_wgrad_bytes_per_point": (I64, [AP]),
     "nerfb200_num_linear": (I64, [AP]),
     "nerfb200_flat_param_count": (I64, [AP]),
     "nerfb200_blob_floats": (I64, [AP]),
@@ -71,6 +69,8 @@ SIGNATURES = {
     "nerfb200_composite_bwd": (I32, [P, P, P, I32, P, P, I64, I32, F32, I32, P, P]),
     "nerfb200_sample_pdf_merge": (I32, [P, P, P, I32, P, I64, I32, I32, P, P, P, P, P]),
     "nerfb200_mlp_bwd": (I32, [AP, P, P, I32, P, I64, I32, P, P, P, P, I32, P]),
+    "nerfb200_mlp_dgrad": (I32, [AP, P, P, P, P, I64, I32, P]),
+    "nerfb200_mlp_wgrad": (I32, [AP, P, I32, P, I64, I32, P, P, P, P, I32, P]),
     "nerfb200_render_workspace_bytes": (I64, [AP, AP, OP, I64, I32]),
     "nerfb200_render_workspace_layout": (I32, [AP, AP, OP, I64, I32, C.POINTER(I64)]),
     "nerfb200_render_fwd": (I32, [AP, AP, OP, P, P, P, I32, I64, P, P, P, P, I32, P, P, P, P, I32, I32, P]),

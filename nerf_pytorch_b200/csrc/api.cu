@@ -93,9 +93,9 @@ int build_plan(const nerfb200_arch_t* a, Plan* p) {
     blob += n;
     g.k_tc = enc_sel == 1 ? k_h : k_h + g.k_enc;
     g.tc_off = blob;
-    blob += 2 * g.k_tc * n;  // hi + lo copies
+    blob += 3 * ((g.k_tc + 15) & ~15) * n / 2;  // three fp16 copies (hs | h | l) of [K padded to 16][n]
     g.tcd_off = blob;
-    blob += 2 * g.k_h * n;
+    blob += 3 * g.k_h * n / 2;                  // three fp16 copies of [n][k_h] for the dgrad chain
     g.cum_n = cum;
     cum += n;
     g.flat_w = flat;
@@ -248,9 +248,7 @@ extern "C" {
 int32_t nerfb200_version(void) { return NERFB200_VERSION; }
 const char* nerfb200_last_error(void) { return g_err; }
 int64_t nerfb200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
-void nerfb200_debug_tc_profile(void* buf) { set_tc_profile(buf); }
-void nerfb200_debug_tc_flags(int32_t flags) { set_tc_flags(flags); }
-int64_t nerfb200_debug_wgrad_bytes_per_point(const nerfb200_arch_t* arch) {
+int64_t nerfb200_wgrad_bytes_per_point(const nerfb200_arch_t* arch) {
   Plan p;
   if (build_plan(arch, &p) != NERFB200_OK) return -1;
   int64_t floats = 0;
@@ -385,6 +383,30 @@ int32_t nerfb200_mlp_bwd(const nerfb200_arch_t* arch, const float* blob, const f
   }
   return launch_mlp_bwd(p, blob, rays, ray_stride, z, n_rays, n_samples, d_raw, stash, gstash, flat_grad, impl,
                         static_cast<cudaStream_t>(stream));
+}
+
+int32_t nerfb200_mlp_dgrad(const nerfb200_arch_t* arch, const float* blob, const float* d_raw, const float* stash,
+                           float* gstash, int64_t n_points, int32_t impl, void* stream) {
+  Plan p;
+  NB_TRY(build_plan(arch, &p));
+  if (!blob || !d_raw || !stash || !gstash || n_points <= 0) {
+    set_error("mlp_dgrad: null pointer or empty input");
+    return NERFB200_ERR_INVALID;
+  }
+  return launch_mlp_dgrad(p, blob, d_raw, stash, gstash, n_points, impl, static_cast<cudaStream_t>(stream));
+}
+
+int32_t nerfb200_mlp_wgrad(const nerfb200_arch_t* arch, const float* rays, int32_t ray_stride, const float* z,
+                           int64_t n_rays, int32_t n_samples, const float* d_raw, const float* stash,
+                           const float* gstash, float* flat_grad, int32_t impl, void* stream) {
+  Plan p;
+  NB_TRY(build_plan(arch, &p));
+  if (!rays || !z || !d_raw || !stash || !gstash || !flat_grad || n_rays <= 0 || n_samples <= 0) {
+    set_error("mlp_wgrad: null pointer or empty input");
+    return NERFB200_ERR_INVALID;
+  }
+  return launch_mlp_wgrad(p, rays, ray_stride, z, n_rays, n_samples, d_raw, stash, gstash, flat_grad, impl,
+                          static_cast<cudaStream_t>(stream));
 }
 
 int32_t nerfb200_composite_fwd(const float* raw, const float* z, const float* rays, int32_t ray_stride,

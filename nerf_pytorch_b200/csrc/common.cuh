@@ -86,6 +86,12 @@ int launch_mlp_fwd_simt(const Plan& p, const float* blob, const float* rays, int
 int launch_mlp_bwd(const Plan& p, const float* blob, const float* rays, int ray_stride, const float* z,
                    int64_t n_rays, int n_samples, const float* d_raw, const float* stash, float* gstash,
                    float* flat_grad, int impl, cudaStream_t s);
+// the two halves of launch_mlp_bwd (stage-level entry points: tests and per-kernel timing)
+int launch_mlp_dgrad(const Plan& p, const float* blob, const float* d_raw, const float* stash, float* gstash, int64_t P,
+                     int impl, cudaStream_t s);
+int launch_mlp_wgrad(const Plan& p, const float* rays, int ray_stride, const float* z, int64_t n_rays, int n_samples,
+                     const float* d_raw, const float* stash, const float* gstash, float* flat_grad, int impl,
+                     cudaStream_t s);
 int launch_dgrad_tc(const Plan& p, const float* blob, const float* d_raw, const float* stash, float* gstash,
                     int64_t P, cudaStream_t s);
 int launch_wgrad_tc(const Plan& p, const float* rays, int ray_stride, const float* z, int64_t n_rays, int n_samples,
@@ -101,10 +107,7 @@ int launch_sample_pdf_merge(const float* z_coarse, const float* weights_coarse, 
                             float* z_samples, int32_t* inds, float* cdf_out, cudaStream_t s);
 int launch_adam(float* p, const float* g, float* m, float* v, int64_t n, int step, float lr, float b1, float b2,
                 float eps, float grad_scale, cudaStream_t s);
-// tcgen05 path (mlp_tc.cu)
-void set_tc_profile(void* p);
-void set_tc_flags(int f);
-int get_tc_flags();
+// tcgen05 path (mlp_tc.cu, mlp_tc_bwd.cu)
 int launch_mlp_fwd_tc(const Plan& p, const float* blob, const float* rays, int ray_stride, const float* z,
                       int64_t n_rays, int n_samples, float* raw, float* stash, cudaStream_t s);
 

@@ -650,21 +650,27 @@ int launch_wgrad_simt(const Plan& p, const float* rays, int ray_stride, const fl
   return check_cuda(cudaGetLastError(), "mlp_bwd_wgrad launch");
 }
 
+int launch_mlp_dgrad(const Plan& p, const float* blob, const float* d_raw, const float* stash, float* gstash, int64_t P,
+                     int impl, cudaStream_t s) {
+  return (impl == 1 && p.hidden == 128) ? launch_dgrad_tc(p, blob, d_raw, stash, gstash, P, s)
+                                        : launch_dgrad_simt(p, blob, d_raw, stash, gstash, P, s);
+}
+
+int launch_mlp_wgrad(const Plan& p, const float* rays, int ray_stride, const float* z, int64_t n_rays, int n_samples,
+                     const float* d_raw, const float* stash, const float* gstash, float* flat_grad, int impl,
+                     cudaStream_t s) {
+  if (impl == 1 && p.hidden == 128)
+    return launch_wgrad_tc(p, rays, ray_stride, z, n_rays, n_samples, stash, gstash, d_raw, flat_grad, s);
+  return launch_wgrad_simt(p, rays, ray_stride, z, n_samples, d_raw, stash, gstash, n_rays * n_samples, flat_grad, 0,
+                           wg_item_count(p), s);
+}
+
 int launch_mlp_bwd(const Plan& p, const float* blob, const float* rays, int ray_stride, const float* z,
                    int64_t n_rays, int n_samples, const float* d_raw, const float* stash, float* gstash,
                    float* flat_grad, int impl, cudaStream_t s) {
-  const int64_t P = n_rays * n_samples;
-  const int dbg = get_tc_flags();  // timing experiments only: 4 = no dgrad launch, 8 = no wgrad launch
-  int rc = NERFB200_OK;
-  if (!(dbg & 4))
-    rc = (impl == 1 && p.hidden == 128) ? launch_dgrad_tc(p, blob, d_raw, stash, gstash, P, s)
-                                        : launch_dgrad_simt(p, blob, d_raw, stash, gstash, P, s);
-  if (rc || (dbg & 8)) return rc;
-  const int items = wg_item_count(p);
-  if (impl == 1 && p.hidden == 128) {
-    return launch_wgrad_tc(p, rays, ray_stride, z, n_rays, n_samples, stash, gstash, d_raw, flat_grad, s);
-  }
-  return launch_wgrad_simt(p, rays, ray_stride, z, n_samples, d_raw, stash, gstash, P, flat_grad, 0, items, s);
+  int rc = launch_mlp_dgrad(p, blob, d_raw, stash, gstash, n_rays * n_samples, impl, s);
+  if (rc) return rc;
+  return launch_mlp_wgrad(p, rays, ray_stride, z, n_rays, n_samples, d_raw, stash, gstash, flat_grad, impl, s);
 }
 
 }  // namespace nerfb200

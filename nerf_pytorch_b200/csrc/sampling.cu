@@ -222,12 +222,12 @@ __global__ void pack_kernel(Plan p, const float* __restrict__ flat, float* __res
       } else if (idx >= g.b_off && idx < g.b_off + g.n) {
         val = flat[g.flat_b + (idx - g.b_off)];
         found = true;
-      } else if (idx >= g.tc_off && idx < g.tc_off + 2 * g.k_tc * g.n) {
-        // forward operand, fp16 x 2 split: [k-step of 16][hi|lo][slab 0|1][n][8 halves]; this float slot holds the
-        // halves of (n, k) and (n, k + 1) with k = kstep*16 + slab*8 + 2j (low half = k).  K is padded to a multiple
-        // of 16 with zeros; the region is 2 k_tc n floats, its tail stays zero.
+      } else if (idx >= g.tc_off && idx < g.tc_off + 3 * ((g.k_tc + 15) & ~15) * g.n / 2) {
+        // forward operand, three fp16 copies (tc_common.cuh split_w3): [k-step of 16][hs|h|l][slab 0|1][n][8 halves];
+        // this float slot holds the halves of (n, k) and (n, k + 1) with k = kstep*16 + slab*8 + 2j (low half = k).
+        // K is padded to a multiple of 16 with zeros.
         const int e = idx - g.tc_off;
-        const int per_step = 16 * g.n;
+        const int per_step = 24 * g.n;
         const int ks = e / per_step, r = e - ks * per_step;
         const int part = r / (8 * g.n), r2 = r - part * 8 * g.n;
         const int slab = r2 / (4 * g.n), r3 = r2 - slab * 4 * g.n;
@@ -236,15 +236,15 @@ __global__ void pack_kernel(Plan p, const float* __restrict__ flat, float* __res
         float w0 = 0.f, w1 = 0.f;
         if (k < g.k_tc && (k < g.k_h || k - g.k_h < g.enc_real)) w0 = flat[g.flat_w + nn * in_real + k];
         if (k + 1 < g.k_tc && (k + 1 < g.k_h || k + 1 - g.k_h < g.enc_real)) w1 = flat[g.flat_w + nn * in_real + k + 1];
-        uint32_t hi, lo;
-        tc::split_f16x2(w0, w1, hi, lo);
-        val = __uint_as_float(part == 0 ? hi : lo);
+        uint32_t hs, h, l;
+        tc::split_w3(w0, w1, hs, h, l);
+        val = __uint_as_float(part == 0 ? hs : (part == 1 ? h : l));
         found = true;
-      } else if (idx >= g.tcd_off && idx < g.tcd_off + 2 * g.k_h * g.n) {
-        // dgrad operand, fp16 x 2 split: [k-step of 16 over n][hi|lo][slab 0|1][k < k_h][8 halves]; this float slot
-        // holds W[n][k] and W[n + 1][k] with n = kstep*16 + slab*8 + 2j (the tail of the region stays zero)
+      } else if (idx >= g.tcd_off && idx < g.tcd_off + 3 * g.k_h * g.n / 2) {
+        // dgrad operand, three fp16 copies: [k-step of 16 over n][hs|h|l][slab 0|1][k < k_h][8 halves]; this float
+        // slot holds W[n][k] and W[n + 1][k] with n = kstep*16 + slab*8 + 2j
         const int e = idx - g.tcd_off;
-        const int per_step = 16 * g.k_h;
+        const int per_step = 24 * g.k_h;
         const int ks = e / per_step, r = e - ks * per_step;
         const int part = r / (8 * g.k_h), r2 = r - part * 8 * g.k_h;
         const int slab = r2 / (4 * g.k_h), r3 = r2 - slab * 4 * g.k_h;
@@ -252,9 +252,9 @@ __global__ void pack_kernel(Plan p, const float* __restrict__ flat, float* __res
         const int nn = ks * 16 + slab * 8 + 2 * j;
         const float w0 = nn < g.n ? flat[g.flat_w + nn * in_real + k] : 0.f;
         const float w1 = nn + 1 < g.n ? flat[g.flat_w + (nn + 1) * in_real + k] : 0.f;
-        uint32_t hi, lo;
-        tc::split_f16x2(w0, w1, hi, lo);
-        val = __uint_as_float(part == 0 ? hi : lo);
+        uint32_t hs, h, l;
+        tc::split_w3(w0, w1, hs, h, l);
+        val = __uint_as_float(part == 0 ? hs : (part == 1 ? h : l));
         found = true;
       }
     }

@@ -109,18 +109,30 @@ __device__ __forceinline__ void mma_ts_f16(uint32_t d, uint32_t a_tmem, uint64_t
       "r"(a_tmem), "l"(b), "r"(idesc), "r"(acc)
       : "memory");
 }
-// fp16 x 2 split of a pair of fp32 values: hi = fp16(x) (saturating), lo = fp16((x - hi) * 2^11); both packed with
-// the FIRST value in the low half (= the lower K index of a 16-bit tensor-memory / shared-memory operand).
+// fp16 x 2 split of a pair of fp32 values: hi = fp16(x), lo = fp16((x - hi) * 2^11); both packed with the FIRST
+// value in the low half (= the lower K index of a 16-bit tensor-memory / shared-memory operand).
 // The residual is scaled by 2^11 so that it is a NORMAL fp16 number whenever hi is (it would be subnormal below
 // |x| = 0.125 otherwise and the split would degrade to 3e-8 absolute resolution): x = hi + lo * 2^-11 carries 22
-// significant bits for 6.1e-5 <= |x| < 65504 and resolves 1.5e-11 absolutely below (tests/test_host_cpu.py).  The cross terms hi*lo and lo*hi therefore accumulate into a second
-// accumulator that the epilogue folds in with the factor 2^-11.
+// significant bits for 6.1e-5 <= |x| < 65504 and resolves 1.5e-11 absolutely below (tests/test_host_cpu.py).
+// Conversions do NOT saturate: a value beyond the fp16 range becomes +-inf, the products turn into inf / NaN and
+// the render output is visibly non-finite instead of silently clamped.
+// Single-accumulator scheme of the chain kernels: the B operand (weights) comes in THREE copies
+//     hs = w_hi * 2^11,   h = w_hi,   l = (w - w_hi) * 2^11          (all fp16; |w| < 32 or hs overflows to inf)
+// and one k-step issues  a_hi*hs + a_lo*h + a_hi*l  =  2^11 * (a*w)  into ONE fp32 accumulator.
 constexpr float kLoScale = 2048.f, kLoInv = 1.f / 2048.f;
 __device__ __forceinline__ void split_f16x2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
-  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
   float h0, h1;
   asm("{\n.reg .b16 a, b;\nmov.b32 {a, b}, %2;\ncvt.f32.f16 %0, a;\ncvt.f32.f16 %1, b;\n}\n" : "=f"(h0), "=f"(h1) : "r"(hi));
-  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"((x1 - h1) * kLoScale), "f"((x0 - h0) * kLoScale));
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"((x1 - h1) * kLoScale), "f"((x0 - h0) * kLoScale));
+}
+// the three weight copies of one pair (same packing)
+__device__ __forceinline__ void split_w3(float w0, float w1, uint32_t& hs, uint32_t& h, uint32_t& l) {
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(w1), "f"(w0));
+  float h0, h1;
+  asm("{\n.reg .b16 a, b;\nmov.b32 {a, b}, %2;\ncvt.f32.f16 %0, a;\ncvt.f32.f16 %1, b;\n}\n" : "=f"(h0), "=f"(h1) : "r"(h));
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hs) : "f"(h1 * kLoScale), "f"(h0 * kLoScale));
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(l) : "f"((w1 - h1) * kLoScale), "f"((w0 - h0) * kLoScale));
 }
 __device__ __forceinline__ float f16_lo_to_f32(uint32_t pair) {
   float f;

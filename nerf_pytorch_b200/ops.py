@@ -203,6 +203,32 @@ def mlp_bwd(arch: ArchSpec, blob, rays, z, d_raw, stash, impl=IMPL_SIMT):
     return flat_grad, gstash
 
 
+def mlp_dgrad(arch: ArchSpec, blob, d_raw, stash, impl=IMPL_SIMT, gstash=None):
+    """First half of mlp_bwd: the pre-activation gradients of every layer (the gradient stash)."""
+    lib = _lib.load()
+    if gstash is None:
+        gstash = torch.empty_like(stash)
+    _lib.check(lib.nerfb200_mlp_dgrad(C.byref(arch.c_struct()), _ptr(blob), _ptr(d_raw), _ptr(stash), _ptr(gstash),
+                                      d_raw.numel() // 4, impl, _stream()), "mlp_dgrad")
+    return gstash
+
+
+def mlp_wgrad(arch: ArchSpec, rays, z, d_raw, stash, gstash, impl=IMPL_SIMT, flat_grad=None):
+    """Second half of mlp_bwd: dW = dY^T X over all points, accumulated into ``flat_grad``."""
+    lib = _lib.load()
+    n, s = z.shape
+    if flat_grad is None:
+        flat_grad = torch.zeros(arch.flat_param_count(), dtype=torch.float32, device=z.device)
+    _lib.check(lib.nerfb200_mlp_wgrad(C.byref(arch.c_struct()), _ptr(rays), rays.shape[1], _ptr(z), n, s, _ptr(d_raw),
+                                      _ptr(stash), _ptr(gstash), _ptr(flat_grad), impl, _stream()), "mlp_wgrad")
+    return flat_grad
+
+
+def wgrad_bytes_per_point(arch: ArchSpec) -> int:
+    """HBM bytes the tcgen05 wgrad kernel reads per point (one dY row + one X row per work item)."""
+    return int(_lib.load().nerfb200_wgrad_bytes_per_point(C.byref(arch.c_struct())))
+
+
 def composite_fwd(raw, z, rays, noise, noise_std, white_bkgd, want_weights=True):
     lib = _lib.load()
     n, s = z.shape

@@ -329,26 +329,26 @@ def run_ours(args):
             tb = t_alone(lambda: ops.mlp_bwd(arch, blob, rays, z, G, stash, impl=impl))
             achb = 2 * flops_fwd / (tb * 1e-3) / 1e12
             roof_bwd = {"kernel": "mlp_bwd (dgrad + wgrad kernels, fine pass)", "bound": "tensor", "achieved": achb,
-                        "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achb / peaks["bf16_tflops"], "ms": tb}
-            # the two backward kernels apart (stage-level entry points of the C ABI)
-            gst = ops.mlp_dgrad(arch, blob, G, stash, impl=impl)
-            fg = torch.zeros(arch.flat_param_count(), dtype=torch.float32, device=dev)
-            t_dg = t_alone(lambda: ops.mlp_dgrad(arch, blob, G, stash, impl=impl, gstash=gst))
-            t_wg = t_alone(lambda: ops.mlp_wgrad(arch, rays, z, G, stash, gst, impl=impl, flat_grad=fg))
-            roof_bwd["dgrad_ms"] = t_dg
-            roof_bwd["wgrad_ms"] = t_wg
-            if args.kernels == "tc" and impl == 1:
-                bpp = ops.wgrad_bytes_per_point(arch)
-                wbytes = float(bpp) * RAYS_PER_GPU * (NC + NF)
-                tr = None
-                if os.path.exists(summ):
-                    tr = json.load(open(summ)).get(f"mlp_wgrad_tc_{args.arch}_dram_bytes")
-                roof_bwd["wgrad"] = {"kernel": "mlp_wgrad_tc (fine pass)", "bound": "hbm",
-                                     "achieved": wbytes / (t_wg * 1e-3) / 1e9, "peak": peaks["hbm_gbs"],
-                                     "peak_source": f"{peak_kind} copy bandwidth", "unit": "GB/s",
-                                     "frac": wbytes / (t_wg * 1e-3) / 1e9 / peaks["hbm_gbs"],
-                                     "algorithmic_bytes": wbytes, "traffic": tr, "ms": t_wg}
-            del stash, raw, G, gst, fg
+                        "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achb / peaks["bf16_tflops"], "ms": tb,
+                        "traffic": None}
+            if impl == ops.IMPL_TC:
+                # one fused kernel (data-gradient chain + all weight gradients): tensor-bound; its HBM side is the
+                # activation tiles it streams back (algorithmic bytes from the library)
+                bbytes = float(ops.bwd_bytes_per_point(arch)) * RAYS_PER_GPU * (NC + NF)
+                roof_bwd["kernel"] = "mlp_bwd_tc (fused dgrad + wgrad, fine pass)"
+                roof_bwd["peak_source"] = f"{peak_kind} bf16 cuBLAS burst"
+                roof_bwd["algorithmic_flops"] = 2 * flops_fwd
+                roof_bwd["hbm"] = {"algorithmic_bytes": bbytes, "achieved": bbytes / (tb * 1e-3) / 1e9,
+                                   "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                   "frac": bbytes / (tb * 1e-3) / 1e9 / peaks["hbm_gbs"]}
+            else:
+                # the two CUDA-core backward kernels apart (stage-level entry points of the C ABI)
+                gst = ops.mlp_dgrad(arch, blob, G, stash, impl=impl)
+                fg = torch.zeros(arch.flat_param_count(), dtype=torch.float32, device=dev)
+                roof_bwd["dgrad_ms"] = t_alone(lambda: ops.mlp_dgrad(arch, blob, G, stash, impl=impl, gstash=gst))
+                roof_bwd["wgrad_ms"] = t_alone(lambda: ops.mlp_wgrad(arch, rays, z, G, stash, gst, impl=impl, flat_grad=fg))
+                del gst, fg
+            del stash, raw, G
 
     # ---- CPU baseline beside it (rank 0, N = 1 only): bounded sample of the same step ----
     cpu = None
@@ -370,9 +370,8 @@ def run_ours(args):
                     "h2d_bytes_per_step": 3 * RAYS_PER_GPU * 3 * 4, "d2h_bytes_per_step": 4},
             "fwd_only": {"value": RAYS_PER_GPU * world / (fwd_ms / 1e3), "unit": "rays/s", "ms_per_step": fwd_ms},
             "gpu_launches": int(launches), "clocks": clocks,
-            # `roofline` = the kernel with the largest share of the step (profiles/r1_final_tc_A1_launch_shares.csv:
-            # wgrad 38 %, dgrad chain 31 %, forward chain 29 %): HBM-bound; the two tensor-bound chain kernels follow
-            "roofline": (roof_bwd or {}).get("wgrad") or roof, "roofline_fwd": roof, "roofline_bwd": roof_bwd,
+            # `roofline` = the kernel with the largest share of the step: the fused backward (tensor-bound)
+            "roofline": roof_bwd or roof, "roofline_fwd": roof, "roofline_bwd": roof_bwd,
             "cpu_baseline": cpu,
         }
         print(json.dumps(line))

@@ -65,8 +65,12 @@ int32_t nerfb200_version(void);
 const char* nerfb200_last_error(void);
 /* number of CUDA kernels this library has launched in this process (all threads) */
 int64_t nerfb200_launch_count(void);
-/* HBM bytes the tcgen05 wgrad kernel reads per point: sum over its work items of one dY row + one X row */
-int64_t nerfb200_wgrad_bytes_per_point(const nerfb200_arch_t* arch);
+/* HBM bytes the tcgen05 backward reads per point: one activation-tile row (4 bytes per feature: fp16 hi + lo) per
+ * weight-gradient job, the ReLU bit masks and d_raw -- the algorithmic traffic of its roofline */
+int64_t nerfb200_bwd_bytes_per_point(const nerfb200_arch_t* arch);
+/* NERFB200_OK if `impl` (0 fp32 CUDA cores, 1 tcgen05) can run this architecture forward AND backward with
+ * n_samples samples per ray, else NERFB200_ERR_UNSUPPORTED (reason in nerfb200_last_error()) */
+int32_t nerfb200_impl_supported(const nerfb200_arch_t* arch, int32_t n_samples, int32_t impl);
 
 /* ---- parameters -------------------------------------------------------------------------------
  * Canonical order of the linears ("slots"): layer1, layers_xyz[0..num_layers-2], then
@@ -101,7 +105,8 @@ int32_t nerfb200_encode(const nerfb200_arch_t* arch, int32_t which, const float*
 /* Fused point generation + encoding + FlexibleNeRFModel.forward (train_utils.py:67, :8-25;
  * models.py:233-256) for every sample of every ray: raw[n_rays][n_samples][4] = [r g b sigma].
  * stash: NULL (inference) or fp32[nerfb200_stash_floats(arch, n_rays*n_samples)] receiving the
- * post-activation output of every hidden linear (needed by the backward entry points).
+ * post-activation output of every hidden linear (needed by the backward entry points; private layout of the
+ * implementation that wrote it: the backward must run with the same impl).
  * impl: 0 = fp32 CUDA cores (bit-faithful fp32 FMA), 1 = tcgen05 tensor cores: every product as a three-term
  * split (fp16 x 2 operands with a 2^11-scaled residual, fp32 accumulation; ~22 significant bits per operand).
  * The split carries 22 bits for magnitudes in 6.1e-5 .. 65504 and resolves 1.5e-11 absolutely below; larger
@@ -136,16 +141,19 @@ int32_t nerfb200_sample_pdf_merge(const float* z_coarse, const float* weights_co
                                   int32_t n_fine, float* z_fine, float* z_samples, int32_t* inds,
                                   float* cdf_out, void* stream);
 
-/* Backward of nerfb200_mlp_fwd w.r.t. the parameters.  d_raw[n_points][4]; stash from the forward.
- * gstash: scratch fp32[nerfb200_stash_floats(...)].  flat_grad: fp32[flat_param_count], ACCUMULATED
- * into (zero it first).  Gradients w.r.t. rays / z are not produced (the reference detaches the
- * fine depths, train_utils.py:103, and rays are data). */
+/* Backward of nerfb200_mlp_fwd w.r.t. the parameters.  d_raw[n_points][4]; stash from the forward (same impl).
+ * gstash: scratch fp32[nerfb200_bwd_scratch_floats(arch, n_points, impl)] (impl 0: the per-layer gradient stash;
+ * impl 1: the L2-resident gradient blob the fused kernel reduces its weight-gradient tiles into).
+ * flat_grad: fp32[flat_param_count], ACCUMULATED into (zero it first).  Gradients w.r.t. rays / z are not
+ * produced (the reference detaches the fine depths, train_utils.py:103, and rays are data). */
+int64_t nerfb200_bwd_scratch_floats(const nerfb200_arch_t* arch, int64_t n_points, int32_t impl);
 int32_t nerfb200_mlp_bwd(const nerfb200_arch_t* arch, const float* blob, const float* rays, int32_t ray_stride,
                          const float* z, int64_t n_rays, int32_t n_samples, const float* d_raw,
                          const float* stash, float* gstash, float* flat_grad, int32_t impl, void* stream);
 /* The two halves of nerfb200_mlp_bwd as separate calls (autograd's accumulation of nn.Linear backward,
  * nerf/models.py:233-256 replayed in reverse): dgrad walks the chain backwards and fills `gstash` with the
- * pre-activation gradients; wgrad reduces dW = dY^T X over all points into `flat_grad` (+=). */
+ * pre-activation gradients; wgrad reduces dW = dY^T X over all points into `flat_grad` (+=).  impl 0 only: the
+ * tcgen05 backward is one fused kernel that never writes the gradients out (NERFB200_ERR_UNSUPPORTED). */
 int32_t nerfb200_mlp_dgrad(const nerfb200_arch_t* arch, const float* blob, const float* d_raw, const float* stash,
                            float* gstash, int64_t n_points, int32_t impl, void* stream);
 int32_t nerfb200_mlp_wgrad(const nerfb200_arch_t* arch, const float* rays, int32_t ray_stride, const float* z,

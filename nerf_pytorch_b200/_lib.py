@@ -55,7 +55,8 @@ SIGNATURES = {
     "nerfb200_version": (I32, []),
     "nerfb200_last_error": (C.c_char_p, []),
     "nerfb200_launch_count": (I64, []),
-    "nerfb200_wgrad_bytes_per_point": (I64, [AP]),
+    "nerfb200_bwd_bytes_per_point": (I64, [AP]),
+    "nerfb200_impl_supported": (I32, [AP, I32, I32]),
     "nerfb200_num_linear": (I64, [AP]),
     "nerfb200_flat_param_count": (I64, [AP]),
     "nerfb200_blob_floats": (I64, [AP]),
@@ -68,6 +69,7 @@ SIGNATURES = {
     "nerfb200_composite_fwd": (I32, [P, P, P, I32, P, I64, I32, F32, I32, P, P, P]),
     "nerfb200_composite_bwd": (I32, [P, P, P, I32, P, P, I64, I32, F32, I32, P, P]),
     "nerfb200_sample_pdf_merge": (I32, [P, P, P, I32, P, I64, I32, I32, P, P, P, P, P]),
+    "nerfb200_bwd_scratch_floats": (I64, [AP, I64, I32]),
     "nerfb200_mlp_bwd": (I32, [AP, P, P, I32, P, I64, I32, P, P, P, P, I32, P]),
     "nerfb200_mlp_dgrad": (I32, [AP, P, P, P, P, I64, I32, P]),
     "nerfb200_mlp_wgrad": (I32, [AP, P, I32, P, I64, I32, P, P, P, P, I32, P]),

@@ -70,6 +70,7 @@ int build_plan(const nerfb200_arch_t* a, Plan* p) {
   }
   p->dim_xyz_pad = pad8(p->dim_xyz);
   p->dim_dir_pad = pad8(p->dim_dir);
+  p->enc_tile_w = (p->dim_xyz + 15) & ~15;
   for (int i = 0; i < NERFB200_MAX_FREQS; ++i) {
     p->freq_xyz[i] = a->freq_xyz[i];
     p->freq_dir[i] = a->freq_dir[i];
@@ -140,7 +141,7 @@ int build_plan(const nerfb200_arch_t* a, Plan* p) {
   }
   p->n_gemm = ng;
   p->enc_cum[0] = cum;
-  cum += p->dim_xyz_pad;
+  cum += p->enc_tile_w;
   p->enc_cum[1] = cum;
   cum += p->dim_dir_pad;
   p->mask_base = cum;
@@ -204,11 +205,18 @@ static void carve(const Plan& pc, const Plan* pf, const nerfb200_render_opts_t& 
   w->z_f = take(fine ? n * ns : 0);
   w->raw_f = take(fine ? n * ns * 4 : 0);
   if (training) {
-    const int64_t sc = n * nc * pc.sum_n;
-    const int64_t sf = fine ? n * ns * pf->sum_n : 0;
+    auto pad128 = [](int64_t v) { return (v + 127) & ~int64_t(127); };
+    const int64_t sc = pad128(n * nc) * pc.sum_n;
+    const int64_t sf = fine ? pad128(n * ns) * pf->sum_n : 0;
     w->stash_c = take(sc);
     w->stash_f = take(sf);
-    w->gstash = take(sc > sf ? sc : sf);
+    // backward scratch: the gradient stash of the CUDA-core path / the gradient blob of the tcgen05 path
+    int64_t gs = sc > sf ? sc : sf;
+    const int64_t bc = pc.hidden == 128 ? bwd_tc_scratch_floats(pc) : 0;
+    const int64_t bf = (fine && pf->hidden == 128) ? bwd_tc_scratch_floats(*pf) : 0;
+    if (bc > gs) gs = bc;
+    if (bf > gs) gs = bf;
+    w->gstash = take(gs);
     w->d_raw = take(n * (fine ? ns : nc) * 4);
   } else {
     w->stash_c = w->stash_f = w->gstash = w->d_raw = off;
@@ -248,16 +256,34 @@ extern "C" {
 int32_t nerfb200_version(void) { return NERFB200_VERSION; }
 const char* nerfb200_last_error(void) { return g_err; }
 int64_t nerfb200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
-int64_t nerfb200_wgrad_bytes_per_point(const nerfb200_arch_t* arch) {
+int64_t nerfb200_bwd_bytes_per_point(const nerfb200_arch_t* arch) {
   Plan p;
   if (build_plan(arch, &p) != NERFB200_OK) return -1;
-  int64_t floats = 0;
-  for (int i = 0, n = wg_item_count(p); i < n; ++i) {
-    int wa, wb;
-    wg_row_widths(p, wg_decode(p, i), &wa, &wb);
-    floats += wa + wb;
+  int64_t bytes = 16;  // d_raw
+  for (int t = 0; t < p.n_gemm; ++t) {
+    const GemmLayer& g = p.g[t];
+    if (g.k_h > 0) bytes += 4 * g.k_h;                               // the layer input tile (hi + lo)
+    if (g.k_enc > 0 && g.enc_sel == 0) bytes += 4 * p.enc_tile_w;    // the encoding tile
+    if (g.relu) bytes += g.n / 8;                                    // ReLU bit mask
   }
-  return 4 * floats;
+  for (int h = 0; h < p.n_head; ++h) bytes += 4 * p.h[h].k;          // the heads' input tiles
+  return bytes;
+}
+
+int32_t nerfb200_impl_supported(const nerfb200_arch_t* arch, int32_t n_samples, int32_t impl) {
+  Plan p;
+  NB_TRY(build_plan(arch, &p));
+  if (impl == 0) return NERFB200_OK;
+  if (impl == 1) return bwd_tc_supported(p, n_samples, "impl_supported");
+  set_error("unknown impl %d", impl);
+  return NERFB200_ERR_INVALID;
+}
+
+int64_t nerfb200_bwd_scratch_floats(const nerfb200_arch_t* arch, int64_t n_points, int32_t impl) {
+  Plan p;
+  if (build_plan(arch, &p) != NERFB200_OK || n_points < 0) return -1;
+  if (impl == 1) return bwd_tc_scratch_floats(p);
+  return ((n_points + 127) & ~int64_t(127)) * p.sum_n;
 }
 
 int64_t nerfb200_num_linear(const nerfb200_arch_t* arch) {
@@ -278,7 +304,7 @@ int64_t nerfb200_blob_floats(const nerfb200_arch_t* arch) {
 int64_t nerfb200_stash_floats(const nerfb200_arch_t* arch, int64_t n_points) {
   Plan p;
   if (build_plan(arch, &p) != NERFB200_OK || n_points < 0) return -1;
-  return n_points * p.sum_n;
+  return ((n_points + 127) & ~int64_t(127)) * p.sum_n;  // whole 128-point tiles (the tcgen05 path stores tiles)
 }
 
 int32_t nerfb200_flat_layout(const nerfb200_arch_t* arch, int32_t slot, int64_t* w_off, int64_t* b_off,

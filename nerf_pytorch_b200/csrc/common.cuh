@@ -57,10 +57,11 @@ struct Plan {
   int n_trunk;  // gemm layers 0..n_trunk-1 are layer1 + layers_xyz
   int n_head;
   int hidden;
-  int sum_n;  // floats stashed per point: every gemm layer's output + the two padded encodings
-  int enc_cum[2];  // stash slice of the xyz / direction encoding: base + n_points * enc_cum[sel], width dim_*_pad
+  int sum_n;  // floats stashed per point: every gemm layer's output + the two padded encodings + the mask words
+  int enc_cum[2];  // stash slice of the xyz / direction encoding: base + n_points * enc_cum[sel], width enc_tile_w / dim_dir_pad
   int mask_base;   // stash slice of the ReLU bit masks: base + n_points * (mask_base + g.mask_cum), n/32 words per point
   int dim_xyz, dim_xyz_pad, dim_dir, dim_dir_pad;
+  int enc_tile_w;  // dim_xyz padded to 16: width of the xyz-encoding operand tile of the tcgen05 path (tc_common.cuh)
   int n_freq_xyz, n_freq_dir, inc_xyz, inc_dir;
   int blob_floats, flat_floats;
   int use_viewdirs;
@@ -92,10 +93,13 @@ int launch_mlp_dgrad(const Plan& p, const float* blob, const float* d_raw, const
 int launch_mlp_wgrad(const Plan& p, const float* rays, int ray_stride, const float* z, int64_t n_rays, int n_samples,
                      const float* d_raw, const float* stash, const float* gstash, float* flat_grad, int impl,
                      cudaStream_t s);
-int launch_dgrad_tc(const Plan& p, const float* blob, const float* d_raw, const float* stash, float* gstash,
-                    int64_t P, cudaStream_t s);
-int launch_wgrad_tc(const Plan& p, const float* rays, int ray_stride, const float* z, int64_t n_rays, int n_samples,
-                    const float* stash, const float* gstash, const float* d_raw, float* flat_grad, cudaStream_t s);
+// tcgen05 backward (mlp_tc_bwd.cu): data-gradient chain + every weight gradient in one kernel; `scratch` holds the
+// L2-resident gradient blob (bwd_tc_scratch_floats) the weight-gradient tiles are reduced into
+int launch_mlp_bwd_tc(const Plan& p, const float* blob, const float* rays, int ray_stride, int64_t n_rays, int n_samples,
+                      const float* d_raw, const float* stash, float* scratch, float* flat_grad, cudaStream_t s);
+int64_t bwd_tc_scratch_floats(const Plan& p);
+int tc_supported(const Plan& p, int n_samples, const char* what);      // forward
+int bwd_tc_supported(const Plan& p, int n_samples, const char* what);  // forward + backward
 int launch_composite_fwd(const float* raw, const float* z, const float* rays, int ray_stride, const float* noise,
                          int64_t n_rays, int n_samples, float noise_std, int white_bkgd, float* out,
                          float* weights, cudaStream_t s);

@@ -650,24 +650,33 @@ int launch_wgrad_simt(const Plan& p, const float* rays, int ray_stride, const fl
   return check_cuda(cudaGetLastError(), "mlp_bwd_wgrad launch");
 }
 
+// The two halves of the CUDA-core backward as stage-level entry points.  The tcgen05 backward is one fused kernel
+// (mlp_tc_bwd.cu) that never materialises the gradient stash, so impl 1 has no halves.
 int launch_mlp_dgrad(const Plan& p, const float* blob, const float* d_raw, const float* stash, float* gstash, int64_t P,
                      int impl, cudaStream_t s) {
-  return (impl == 1 && p.hidden == 128) ? launch_dgrad_tc(p, blob, d_raw, stash, gstash, P, s)
-                                        : launch_dgrad_simt(p, blob, d_raw, stash, gstash, P, s);
+  if (impl == 1) {
+    set_error("mlp_dgrad: impl=1 (tcgen05) fuses dgrad and wgrad into one kernel; call nerfb200_mlp_bwd");
+    return NERFB200_ERR_UNSUPPORTED;
+  }
+  return launch_dgrad_simt(p, blob, d_raw, stash, gstash, P, s);
 }
 
 int launch_mlp_wgrad(const Plan& p, const float* rays, int ray_stride, const float* z, int64_t n_rays, int n_samples,
                      const float* d_raw, const float* stash, const float* gstash, float* flat_grad, int impl,
                      cudaStream_t s) {
-  if (impl == 1 && p.hidden == 128)
-    return launch_wgrad_tc(p, rays, ray_stride, z, n_rays, n_samples, stash, gstash, d_raw, flat_grad, s);
+  if (impl == 1) {
+    set_error("mlp_wgrad: impl=1 (tcgen05) fuses dgrad and wgrad into one kernel; call nerfb200_mlp_bwd");
+    return NERFB200_ERR_UNSUPPORTED;
+  }
   return launch_wgrad_simt(p, rays, ray_stride, z, n_samples, d_raw, stash, gstash, n_rays * n_samples, flat_grad, 0,
                            wg_item_count(p), s);
 }
 
+// `gstash`: impl 0: the gradient stash (stash-sized); impl 1: scratch for the gradient blob (bwd_tc_scratch_floats)
 int launch_mlp_bwd(const Plan& p, const float* blob, const float* rays, int ray_stride, const float* z,
                    int64_t n_rays, int n_samples, const float* d_raw, const float* stash, float* gstash,
                    float* flat_grad, int impl, cudaStream_t s) {
+  if (impl == 1) return launch_mlp_bwd_tc(p, blob, rays, ray_stride, n_rays, n_samples, d_raw, stash, gstash, flat_grad, s);
   int rc = launch_mlp_dgrad(p, blob, d_raw, stash, gstash, n_rays * n_samples, impl, s);
   if (rc) return rc;
   return launch_mlp_wgrad(p, rays, ray_stride, z, n_rays, n_samples, d_raw, stash, gstash, flat_grad, impl, s);

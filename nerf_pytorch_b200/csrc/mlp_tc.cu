@@ -1,25 +1,21 @@
-// mlp_tc.cu -- tcgen05 (5th-generation tensor core) implementation of the two layer-chained kernels
-//   forward : points -> positional encoding -> FlexibleNeRFModel   (nerf/train_utils.py:67, :8-25; nerf/models.py:233-256)
-//   dgrad   : the same chain walked backwards, G_t = (G_s W_s[:, :hidden] + d_raw W_head) (.) relu'(layer t)
-// for hidden_size 128, fp32-faithful through a 3-term split of every product
+// mlp_tc.cu -- tcgen05 (5th-generation tensor core) implementation of the layer-chained forward kernel
+//   points -> positional encoding -> FlexibleNeRFModel   (nerf/train_utils.py:67, :8-25; nerf/models.py:233-256)
+// (the backward lives in mlp_tc_bwd.cu) for hidden_size 128, fp32-faithful through a 3-term split of every product
 //     a * w  ~=  a_hi*w_hi + a_lo*w_hi + a_hi*w_lo          
 // on tcgen05.mma.kind::f16 (K = 16 per instruction): both operands are fp16 pairs (hi = fp16(x), lo = fp16((x - hi) 2^11),
 // 22 significant bits, tc_common.cuh split_f16x2); the weights come in three pre-scaled copies (hs | h | l, split_w3) so
 // that the three products of a k-step land at the SAME scale 2^11 in ONE fp32 accumulator in tensor memory.
-//   forward: the A operand holds activation / 16 (fp16 range 65504 -> 1.05e6: the shipped lego checkpoints reach 6e4);
-//            conversions do not saturate, an out-of-range value turns the output into inf / NaN instead of clamping.
-//   dgrad  : gradients span many decades ACROSS points (a sample's compositing weight scales its whole row), so
-//            every row runs in its own power-of-two scale: d_raw[row] is scaled to max-abs in [2^-4, 2^-3) on load, the
-//            chain is linear in it, and the gradient stash receives the exactly unscaled fp32 values.
+// The A operand holds activation / 16 (fp16 range 65504 -> 1.05e6: the shipped lego checkpoints reach 6e4);
+// conversions do not saturate, an out-of-range value turns the output into inf / NaN instead of clamping.
 //
 // Persistent kernels, one CTA per SM, 320 threads, TWO 128-point tiles in flight per CTA ("slots"): while the
 // epilogue warps work on one slot's accumulator, the tensor pipe runs the other slot's layer.
 //   warps 0-7  prologue/epilogue: thread (row = tid % 128, half = tid / 128) owns half of the columns of row
 //              `row` of a tile (= TMEM lane row).  Per layer: tcgen05.ld the fp32 accumulator, one FFMA for scale +
-//              bias, ReLU (forward) or + head term / ReLU mask (dgrad), narrow heads as register dot products, split
-//              into fp16 hi + lo and tcgen05.st back into tensor memory as the NEXT layer's A operand; training
-//              outputs (activation stash, ReLU bit mask, gradient stash) leave through a 64 KB staging tile and
-//              ONE cp.async.bulk store per layer.
+//              bias, ReLU, narrow heads as register dot products, split into fp16 hi + lo and tcgen05.st back into
+//              tensor memory as the NEXT layer's A operand.  Training: the SAME hi / lo registers are also stored
+//              to the activation stash as an operand tile (tc_common.cuh "Operand tiles": eight lanes write one
+//              full 128-byte line), plus one ReLU bit per activation; no staging buffer, no extra barrier.
 //   warp 8     MMA issuer: one elected lane, tcgen05.mma.kind::f16 M=128, N=128|64, K=16, three per k-step;
 //              A from tensor memory (hidden activations / gradients) or shared memory (encodings), B = the three
 //              weight copies from the shared-memory ring (two k-steps = 24 KB per stage).
@@ -41,24 +37,20 @@ constexpr int kThreadsTc = 320;
 constexpr int kStepsPerStage = 2;                    // k-steps per ring stage
 constexpr int kStageBytes = kStepsPerStage * 96 * 128;  // 24 KB: 3 copies x 2 slabs x 128 rows x 16 B per k-step
 constexpr int kMaxStages = 6;
-constexpr int kSlabBytes = 2048;                     // 128 rows x 16 B
-constexpr int kEncBytes = 16 * kSlabBytes;           // per slot: 8 slabs hi (K <= 64), 8 slabs lo
+constexpr int kEncBytes = 32768;                     // per slot: encoding operand tile, hi block then lo block (<= 64 wide)
 constexpr int kMaxRaysPerTile = 10;
 constexpr uint32_t kTmemCols = 512, kSlotCols = 256;
 constexpr uint32_t kColAcc = 0, kColAhi = 128, kColAlo = 192;
-constexpr float kActScale = 0.0625f, kActInv = 16.f;  // forward A operands hold activation / 16
 constexpr int kSmemLimit = 232448 - 1024;            // 227 KB minus the alignment slack
 
 // Shared memory map (bytes from the 1 KB-aligned base), computed identically on host and device.
 struct SmemMap {
-  int enc, ring, stage, bias, headw, viewb, encd, hpart, bars, total, n_stages;
+  int enc, ring, bias, headw, viewb, encd, hpart, bars, total, n_stages;
 };
-__host__ __device__ inline SmemMap smem_map(const Plan& p, bool training) {
+__host__ __device__ inline SmemMap smem_map(const Plan& p) {
   SmemMap m;
-  m.enc = 0;                                        // 2 slots x 32 KB: encodings as fp16 K-major slabs (hi | lo)
-  m.stage = m.enc + 2 * kEncBytes;                  // 64 KB stash staging tile (training); its first 32 KB double as
-                                                    // the per-warp transpose tiles of the encoding stash
-  int off = m.stage + (training ? 65536 : 0);
+  m.enc = 0;                                        // 2 slots x 32 KB: encodings as fp16 operand tiles (hi | lo)
+  int off = m.enc + 2 * kEncBytes;
   m.bias = off;      off += p.enc_cum[0] * 4;       // sum of n over the gemm layers (bias / 16)
   m.headw = off;     off += (4 * 128 + 3 * 64 + 16) * 4;
   m.viewb = off;     off += 2 * kMaxRaysPerTile * 64 * 4;
@@ -74,39 +66,8 @@ __host__ __device__ inline SmemMap smem_map(const Plan& p, bool training) {
   return m;
 }
 
-__device__ __forceinline__ void epi_bar256() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
-
-// 32 rows (lane = row) x 32 fp32 columns held one row per lane -> global rows of `ld` floats, coalesced:
-// swizzled 16-byte chunks through a 4 KB per-warp tile, then 4 rows x 128 B per store instruction.
-__device__ __forceinline__ void store_tile_coalesced(float* tbuf, const float (&x)[32], float* gdst, int ld, int lane,
-                                                     int rows_valid) {
-#pragma unroll
-  for (int q = 0; q < 8; ++q)
-    *reinterpret_cast<float4*>(tbuf + lane * 32 + ((q ^ (lane & 7)) << 2)) =
-        make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
-  __syncwarp();
-  const int q = lane & 7;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int r = 4 * i + (lane >> 3);
-    const float4 v = *reinterpret_cast<const float4*>(tbuf + r * 32 + ((q ^ (r & 7)) << 2));
-    if (r < rows_valid) __stcs(reinterpret_cast<float4*>(gdst + (size_t)r * ld + 4 * q), v);
-  }
-  __syncwarp();
-}
-
-struct Pipe {  // role-local ring state
-  uint32_t stage = 0, phase = 0;
-  __device__ __forceinline__ void advance(uint32_t n_stages) {
-    if (++stage == n_stages) { stage = 0; phase ^= 1; }
-  }
-};
-
-// The fixed interleaving of the two slots' events.  A tile is E events; event e of a tile is followed by MMA #e
-// (e < E - 1) whose A operand that event wrote, and event e >= 1 consumes the accumulator of MMA #(e - 1).
-//   forward: E = n_gemm + 1: event 0 = prologue (encodings), event e = epilogue of layer e - 1; MMA #e = layer e
-//   dgrad  : E = n_gemm    : event e = gradient of layer t = n_gemm - 1 - e (event 0 has no MMA input);
-//                            MMA #e contracts G_{t} with the weights of layer s = n_gemm - 1 - e
+// The fixed interleaving of the two slots' events.  A tile is E = n_gemm + 1 events: event 0 = prologue (encodings),
+// event e = epilogue of layer e - 1; it is followed by MMA #e = layer e (e < n_gemm) whose A operand it wrote.
 struct Seq {
   int E, off1, n0, n1, ticks;
   __device__ __forceinline__ Seq(int events, int my_tiles) {
@@ -127,40 +88,29 @@ struct Seq {
   }
 };
 
-// what the MMA after event e of a tile contracts (both modes): weights, shapes
+// what MMA #e (= layer e) contracts: weights, shapes
 struct MmaInfo {
   const uint8_t* src;   // blob copy of the layer's weights (three fp16 copies, k-step major)
   uint32_t kbytes;      // bytes of one k-step
   int ksteps, ksteps_h; // k-steps, of which the first ksteps_h read A from tensor memory (the rest: encodings)
   int n_mma;            // N of the instruction
 };
-template <int kMode>
 __device__ __forceinline__ MmaInfo mma_info(const Plan& p, const float* blob, int e) {
   MmaInfo mi;
-  if (kMode == 0) {
-    const GemmLayer& g = p.g[e];
-    mi.src = reinterpret_cast<const uint8_t*>(blob + g.tc_off);
-    mi.n_mma = g.n;
-    mi.ksteps = (g.k_tc + 15) >> 4;
-    mi.ksteps_h = g.k_h >> 4;
-  } else {
-    const GemmLayer& g = p.g[p.n_gemm - 1 - e];
-    mi.src = reinterpret_cast<const uint8_t*>(blob + g.tcd_off);
-    mi.n_mma = g.k_h;
-    mi.ksteps = g.n >> 4;
-    mi.ksteps_h = mi.ksteps;
-  }
+  const GemmLayer& g = p.g[e];
+  mi.src = reinterpret_cast<const uint8_t*>(blob + g.tc_off);
+  mi.n_mma = g.n;
+  mi.ksteps = (g.k_tc + 15) >> 4;
+  mi.ksteps_h = g.k_h >> 4;
   mi.kbytes = 96u * (uint32_t)mi.n_mma;
   return mi;
 }
 
 // per-slot state an epilogue thread carries across the events of one tile
 struct TileState {
-  int64_t p0 = 0, pt = 0;
+  int64_t p0 = 0, pt = 0, tile = 0;
   bool valid = false;
   int ray_slot = 0;
-  float dr[4] = {0.f, 0.f, 0.f, 0.f};
-  float unscale = 1.f;
   uint32_t acc_phase = 0;
 };
 
@@ -168,104 +118,91 @@ struct TileState {
 
 using namespace tc;
 
-// One 32-column chunk of one row in the epilogue (the hot loop of the chain kernels), specialised at compile time
-// on the number of narrow-head rows reading this layer (kHN: 0, 1, 3, 4) and on training outputs (kTrain).
-//   forward: ys = max(acc * 2^-11 + bias/16, lb) = activation / 16      (lb = 0 with ReLU, -inf without; the bias
-//            already holds the per-ray direction term for layers_dir[0]); head rows accumulate ys * (16 w)
-//   dgrad  : y = (acc * 2^-11 + sum_c d_raw[c] * W_head[c]) masked by the forward ReLU bit
-// then -> fp16 hi / lo -> tensor memory (next layer's A operand).
+// One 32-column chunk of one row in the epilogue (the hot loop), specialised at compile time on the number of
+// narrow-head rows reading this layer (kHN: 0, 1, 3, 4) and on training outputs (kTrain):
+//   ys = max(acc * 2^-11 + bias/16, lb) = activation / 16      (lb = 0 with ReLU, -inf without; the bias already
+//   holds the per-ray direction term for layers_dir[0]); head rows accumulate ys * (16 w);
+// then -> fp16 hi / lo -> tensor memory (next layer's A operand) and, in training, the stash tile.
 struct ChunkArgs {
-  const float* bias;      // fwd: this layer's bias / 16 (or the per-ray bias of layers_dir[0])
-  float lb;               // fwd: ReLU lower bound
-  const float* hw;        // head weights [hn][hk] in smem (fwd: pre-multiplied by 16)
+  const float* bias;      // this layer's bias / 16 (or the per-ray bias of layers_dir[0])
+  float lb;               // ReLU lower bound
+  const float* hw;        // head weights [hn][hk] in smem (pre-multiplied by 16)
   int hk;
-  float hd[4];            // dgrad: d_raw (row-scaled) of the head's columns
-  uint32_t mword_in;      // dgrad: ReLU mask word of this chunk
-  uint32_t* mword_out;    // fwd train: where to store the mask word (or nullptr when the row is out of range)
-  uint8_t* stg_row;       // train: this row inside the staging tile (row * n * 4 bytes in), or nullptr
-  int row7;               // row & 7: the stash chunk swizzle of this row (common.cuh swz_col)
-  float unscale;          // dgrad: 2^-s of this row's power-of-two scale (applied to what goes to the gradient stash)
+  uint32_t* mword_out;    // train: where to store the ReLU mask word (or nullptr when the row is out of range)
+  uint8_t* stash_hi;      // train: this row's first 16-byte piece of the layer's stash tile (hi block), feature block 0
+  int stash_lo_off;       // train: byte offset of the lo block
   uint32_t tmem_hi, tmem_lo;  // destination addresses (already offset to column c0)
   bool has_next;
 };
 
-template <int kMode, int kHN, bool kTrain>
+template <int kHN, bool kTrain>
 __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int c0, const ChunkArgs& a, float (&hacc)[4]) {
   float x[32];
   uint32_t bits = 0;
 #pragma unroll
   for (int j = 0; j < 32; j += 4) {
     float y[4];
-    if (kMode == 0) {
-      const float4 b = *reinterpret_cast<const float4*>(a.bias + c0 + j);
-      y[0] = fmaxf(fmaf(__uint_as_float(v[j]), kLoInv, b.x), a.lb);
-      y[1] = fmaxf(fmaf(__uint_as_float(v[j + 1]), kLoInv, b.y), a.lb);
-      y[2] = fmaxf(fmaf(__uint_as_float(v[j + 2]), kLoInv, b.z), a.lb);
-      y[3] = fmaxf(fmaf(__uint_as_float(v[j + 3]), kLoInv, b.w), a.lb);
+    const float4 b = *reinterpret_cast<const float4*>(a.bias + c0 + j);
+    y[0] = fmaxf(fmaf(__uint_as_float(v[j]), kLoInv, b.x), a.lb);
+    y[1] = fmaxf(fmaf(__uint_as_float(v[j + 1]), kLoInv, b.y), a.lb);
+    y[2] = fmaxf(fmaf(__uint_as_float(v[j + 2]), kLoInv, b.z), a.lb);
+    y[3] = fmaxf(fmaf(__uint_as_float(v[j + 3]), kLoInv, b.w), a.lb);
 #pragma unroll
-      for (int c = 0; c < kHN; ++c) {
-        const float4 w = *reinterpret_cast<const float4*>(a.hw + c * a.hk + c0 + j);
-        hacc[c] = fmaf(y[0], w.x, fmaf(y[1], w.y, fmaf(y[2], w.z, fmaf(y[3], w.w, hacc[c]))));
-      }
-      if (kTrain) {
+    for (int c = 0; c < kHN; ++c) {
+      const float4 w = *reinterpret_cast<const float4*>(a.hw + c * a.hk + c0 + j);
+      hacc[c] = fmaf(y[0], w.x, fmaf(y[1], w.y, fmaf(y[2], w.z, fmaf(y[3], w.w, hacc[c]))));
+    }
+    if (kTrain) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) bits |= (y[q] > 0.f ? 1u : 0u) << (j + q);
-      }
-    } else {
-      y[0] = __uint_as_float(v[j]) * kLoInv; y[1] = __uint_as_float(v[j + 1]) * kLoInv;
-      y[2] = __uint_as_float(v[j + 2]) * kLoInv; y[3] = __uint_as_float(v[j + 3]) * kLoInv;
-#pragma unroll
-      for (int c = 0; c < kHN; ++c) {
-        const float4 w = *reinterpret_cast<const float4*>(a.hw + c * a.hk + c0 + j);
-        const float d = a.hd[c];
-        y[0] = fmaf(d, w.x, y[0]); y[1] = fmaf(d, w.y, y[1]); y[2] = fmaf(d, w.z, y[2]); y[3] = fmaf(d, w.w, y[3]);
-      }
-#pragma unroll
-      for (int q = 0; q < 4; ++q) y[q] = ((a.mword_in >> (j + q)) & 1u) ? y[q] : 0.f;
+      for (int q = 0; q < 4; ++q) bits |= (y[q] > 0.f ? 1u : 0u) << (j + q);
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q) x[j + q] = y[q];
   }
-  if (kMode == 0 && kTrain && a.mword_out) *a.mword_out = bits;
-  if (kTrain && a.stg_row) {
-    const float u = kMode == 1 ? a.unscale : kActInv;  // forward: x holds activation / 16
-#pragma unroll
-    for (int q = 0; q < 8; ++q)
-      *reinterpret_cast<float4*>(a.stg_row + ((((c0 >> 2) + q) ^ a.row7) << 4)) =
-          make_float4(x[4 * q] * u, x[4 * q + 1] * u, x[4 * q + 2] * u, x[4 * q + 3] * u);
-  }
-  if (a.has_next) {
-    // fp16 x 2: two K-adjacent values per tensor-memory column
+  if (kTrain && a.mword_out) *a.mword_out = bits;
+  if (a.has_next || kTrain) {
+    // fp16 x 2: two K-adjacent values per tensor-memory column / per 32-bit word of a stash piece
     uint32_t hi[16], lo[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) split_f16x2(x[2 * j], x[2 * j + 1], hi[j], lo[j]);
-    tmem_st16(a.tmem_hi, hi);
-    tmem_st16(a.tmem_lo, lo);
+    if (a.has_next) {
+      tmem_st16(a.tmem_hi, hi);
+      tmem_st16(a.tmem_lo, lo);
+    }
+    if (kTrain) {
+      // four 16-byte pieces (8 features each) per block; lanes p & 7 = 0..7 of a quarter warp fill one 128-byte line
+      uint8_t* dh = a.stash_hi + (c0 >> 3) * 128;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        __stcs(reinterpret_cast<uint4*>(dh + q * 128), make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]));
+        __stcs(reinterpret_cast<uint4*>(dh + a.stash_lo_off + q * 128),
+               make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]));
+      }
+    }
   }
 }
 
-template <int kMode, bool kTrain>
+template <bool kTrain>
 __device__ __forceinline__ void epilogue_chunk_dispatch(int hn, const uint32_t (&v)[32], int c0, const ChunkArgs& a,
                                                         float (&hacc)[4]) {
   switch (hn) {
-    case 0: epilogue_chunk<kMode, 0, kTrain>(v, c0, a, hacc); break;
-    case 1: epilogue_chunk<kMode, 1, kTrain>(v, c0, a, hacc); break;
-    case 3: epilogue_chunk<kMode, 3, kTrain>(v, c0, a, hacc); break;
-    default: epilogue_chunk<kMode, 4, kTrain>(v, c0, a, hacc); break;
+    case 0: epilogue_chunk<0, kTrain>(v, c0, a, hacc); break;
+    case 1: epilogue_chunk<1, kTrain>(v, c0, a, hacc); break;
+    case 3: epilogue_chunk<3, kTrain>(v, c0, a, hacc); break;
+    default: epilogue_chunk<4, kTrain>(v, c0, a, hacc); break;
   }
 }
 
-// kMode 0: forward, 1: dgrad.  kTrain: the forward also writes the activation stash (dgrad always writes gstash).
-template <int kMode, bool kTrain>
+// kTrain: the forward also writes the activation stash (operand tiles + ReLU bit masks + the encoding tile).
+template <bool kTrain>
 __global__ void __launch_bounds__(kThreadsTc, 1)
-mlp_chain_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob, const float* __restrict__ rays,
-                    int ray_stride, const float* __restrict__ z, int64_t P, int S, int64_t n_tiles,
-                    float* __restrict__ raw,          // fwd: out [P][4];   dgrad: d_raw in (read only)
-                    float* __restrict__ stash,        // fwd: out (kTrain); dgrad: in
-                    float* __restrict__ gstash) {     // dgrad: out
+mlp_fwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob, const float* __restrict__ rays,
+                  int ray_stride, const float* __restrict__ z, int64_t P, int S, int64_t n_tiles,
+                  float* __restrict__ raw,          // out [P][4]
+                  float* __restrict__ stash) {      // out (kTrain)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // 1 KB aligned base
-  const SmemMap mp = smem_map(p, kTrain);
+  const SmemMap mp = smem_map(p);
   float* s_bias = reinterpret_cast<float*>(sm + mp.bias);
   float* s_headw = reinterpret_cast<float*>(sm + mp.headw);
   float* s_viewb = reinterpret_cast<float*>(sm + mp.viewb);
@@ -282,9 +219,11 @@ mlp_chain_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ bl
   uint64_t* bar_acc = bar_a2 + 2;                 // [2]
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_acc + 2);
   const uint32_t n_stages = (uint32_t)mp.n_stages;
-  uint8_t* staging = sm + mp.stage;
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int64_t P_pad = n_tiles * kTileRows;       // the stash sections are sized in whole tiles
+  const int enc_w = p.enc_tile_w;                  // encoding operand tile width (dim_xyz padded to 16)
+  const int enc_half = tile_half_bytes(enc_w);
 
   if (tid == 0) {
     for (int i = 0; i < kMaxStages; ++i) {
@@ -303,15 +242,13 @@ mlp_chain_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ bl
                  "r"(kTmemCols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
-  // biases (/16) + head weights (forward: x16, they multiply activation / 16): once per CTA
-  if (kMode == 0)
-    for (int gi = 0; gi < p.n_gemm; ++gi)
-      for (int i = tid; i < p.g[gi].n; i += kThreadsTc) s_bias[p.g[gi].cum_n + i] = blob[p.g[gi].b_off + i] * kActScale;
+  // biases (/16) + head weights (x16, they multiply activation / 16): once per CTA
+  for (int gi = 0; gi < p.n_gemm; ++gi)
+    for (int i = tid; i < p.g[gi].n; i += kThreadsTc) s_bias[p.g[gi].cum_n + i] = blob[p.g[gi].b_off + i] * kActScale;
   const int hw1 = p.h[0].n_out * p.h[0].k;
   const int hw2 = p.n_head > 1 ? p.h[1].n_out * p.h[1].k : 0;
-  const float hscale = kMode == 0 ? kActInv : 1.f;
-  for (int i = tid; i < hw1; i += kThreadsTc) s_headw[i] = blob[p.h[0].w_off + i] * hscale;
-  for (int i = tid; i < hw2; i += kThreadsTc) s_headw[hw1 + i] = blob[p.h[1].w_off + i] * hscale;
+  for (int i = tid; i < hw1; i += kThreadsTc) s_headw[i] = blob[p.h[0].w_off + i] * kActInv;
+  for (int i = tid; i < hw2; i += kThreadsTc) s_headw[hw1 + i] = blob[p.h[1].w_off + i] * kActInv;
   float* s_headb = s_headw + ((hw1 + hw2 + 3) & ~3);
   if (tid < 4) s_headb[tid] = blob[p.h[0].b_off + tid];
   if (tid >= 4 && tid < 8) s_headb[tid] = p.n_head > 1 ? blob[p.h[1].b_off + tid - 4] : 0.f;
@@ -322,20 +259,20 @@ mlp_chain_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ bl
   const uint32_t tmem = *s_tmem;
 
   const int my_tiles = (n_tiles > blockIdx.x) ? (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
-  const int E = kMode == 0 ? p.n_gemm + 1 : p.n_gemm;
+  const int E = p.n_gemm + 1;
   const int nM = E - 1;
   const Seq seq(E, my_tiles);
 
   if (warp == 9) {
     // ===================== weight producer =====================
-    if (lane == 0) {
+    if ((tid & 31) == 0) {
       Pipe pp;
       const uint64_t pol = l2_policy_evict_last();
       for (int tk = 0; tk < seq.ticks; ++tk) {
         for (int s = 0; s < 2; ++s) {
           int j, e;
           if (!seq.at(tk, s, j, e) || e >= nM) continue;
-          const MmaInfo mi = mma_info<kMode>(p, blob, e);
+          const MmaInfo mi = mma_info(p, blob, e);
           for (int ks = 0; ks < mi.ksteps; ks += kStepsPerStage) {
             const uint32_t bytes = (uint32_t)min(kStepsPerStage, mi.ksteps - ks) * mi.kbytes;
             mbar_wait(&bar_empty[pp.stage], pp.phase ^ 1);
@@ -356,7 +293,7 @@ mlp_chain_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ bl
       for (int s = 0; s < 2; ++s) {
         int j, e;
         if (!seq.at(tk, s, j, e) || e >= nM) continue;
-        const MmaInfo mi = mma_info<kMode>(p, blob, e);
+        const MmaInfo mi = mma_info(p, blob, e);
         const uint32_t idesc = make_idesc_f16(mi.n_mma);
         const uint32_t slab_b = 16u * (uint32_t)mi.n_mma;  // bytes of one weight slab
         const uint32_t t_acc = tmem + s * kSlotCols + kColAcc;
@@ -389,10 +326,10 @@ mlp_chain_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ bl
                   mma_ts_f16(t_acc, t_ahi + 8 * ks, b_hs, idesc, acc0);
                   mma_ts_f16(t_acc, t_alo + 8 * ks, b_h, idesc, 1u);
                   mma_ts_f16(t_acc, t_ahi + 8 * ks, b_l, idesc, 1u);
-                } else {  // encodings: both halves are shared-memory operands (8 slabs hi, 8 slabs lo)
-                  const uint32_t off = (uint32_t)(ks - mi.ksteps_h) * 2 * kSlabBytes;
-                  const uint64_t e_hi_d = make_desc(e_hi + off, kSlabBytes, 128);
-                  const uint64_t e_lo_d = make_desc(e_hi + 8 * kSlabBytes + off, kSlabBytes, 128);
+                } else {  // encodings: K-major view of the operand tile (SBO = next 8 points, LBO = next 8 features)
+                  const uint32_t off = (uint32_t)(ks - mi.ksteps_h) * 256u;
+                  const uint64_t e_hi_d = make_desc(e_hi + off, 128, (uint32_t)(enc_w >> 3) * 128u);
+                  const uint64_t e_lo_d = make_desc(e_hi + enc_half + off, 128, (uint32_t)(enc_w >> 3) * 128u);
                   mma_ss_f16(t_acc, e_hi_d, b_hs, idesc, acc0);
                   mma_ss_f16(t_acc, e_lo_d, b_h, idesc, 1u);
                   mma_ss_f16(t_acc, e_hi_d, b_l, idesc, 1u);
@@ -414,7 +351,6 @@ mlp_chain_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ bl
     // ===================== prologue / epilogue warps =====================
     const int row = tid & 127, half = tid >> 7;
     const uint32_t lane_base = ((uint32_t)((warp & 3) * 32)) << 16;
-    float* tbuf = reinterpret_cast<float*>(staging) + warp * 1024;  // 4 KB per warp (training forward only)
     TileState st0, st1;
 
     auto run_event = [&](const int s, TileState& ts, const int j, const int e) {
@@ -427,43 +363,35 @@ mlp_chain_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ bl
       float* hpart = s_hpart + s * 2 * 128 * 4;
 
       if (e == 0) {
-        // ---------------- new tile ----------------
-        const int64_t tile = blockIdx.x + (int64_t)(2 * j + s) * gridDim.x;
-        ts.p0 = tile * kTileRows;
+        // ================= new tile: encodings of this row -> operand tile (value / 16), the two halves split the
+        // frequencies
+        ts.tile = blockIdx.x + (int64_t)(2 * j + s) * gridDim.x;
+        ts.p0 = ts.tile * kTileRows;
         ts.pt = ts.p0 + row;
         ts.valid = ts.pt < P;
         if (!ts.valid) ts.pt = P - 1;
-      }
-      const int64_t p0 = ts.p0, pt = ts.pt;
-      const bool valid = ts.valid;
-      const int64_t wrow0 = p0 + (warp & 3) * 32;  // first point of this warp's 32-row block
-      const int rows_valid = (int)(P - wrow0 < 32 ? (P - wrow0 < 0 ? 0 : P - wrow0) : 32);
-
-      if (kMode == 0 && e == 0) {
-        // ================= forward prologue: encodings of this row -> E_hi / E_lo (canonical K-major slabs, value / 16);
-        // the two halves split the frequencies
+        const int64_t p0 = ts.p0, pt = ts.pt;
         const int64_t ray = pt / S;
         const int64_t first_ray = p0 / S;
         const int64_t last_pt = (p0 + kTileRows - 1 < P) ? p0 + kTileRows - 1 : P - 1;
         const int n_rays_tile = (int)(last_pt / S - first_ray) + 1;
         ts.ray_slot = (int)(ray - first_ray);
+        if (kTrain) {  // the previous tile's encoding store must have finished reading this buffer
+          if (tid == 0) bulk_wait_read();
+          epi_bar256();
+        }
         {
           const float* rr = rays + ray * ray_stride;
           const float zz = z[pt];
-          // the encoding also goes to the stash for the backward: through the coalesced path below when the
-          // padded width is the usual 64, else element by element
-          float* sx = (kTrain && valid && p.dim_xyz_pad != 64)
-                          ? stash + (size_t)P * p.enc_cum[0] + (size_t)pt * p.dim_xyz_pad : nullptr;
           const int nf = p.n_freq_xyz, mid = nf >> 1;
           const int f0 = half ? mid : 0, f1 = half ? nf : mid;
           const int base = p.inc_xyz ? 3 : 0;
           auto put = [&](int k, float v) {
-            if (sx) sx[k] = v;
             uint32_t hi, lo;
             split_f16x2(v * kActScale, 0.f, hi, lo);  // this element in the low halves
-            const int off = (k >> 3) * kSlabBytes + row * 16 + (k & 7) * 2;
+            const int off = tile_piece(row, k >> 3, enc_w) + (k & 7) * 2;
             *reinterpret_cast<uint16_t*>(e_hi + off) = (uint16_t)hi;
-            *reinterpret_cast<uint16_t*>(e_hi + 8 * kSlabBytes + off) = (uint16_t)lo;
+            *reinterpret_cast<uint16_t*>(e_hi + enc_half + off) = (uint16_t)lo;
           };
           for (int c = 0; c < 3; ++c) {
             const float x = __fadd_rn(rr[c], __fmul_rn(rr[3 + c], zz));  // pts = ro + rd * z (train_utils.py:67)
@@ -475,11 +403,8 @@ mlp_chain_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ bl
               put(base + 6 * f + 3 + c, cs);
             }
           }
-          if (half == 1) {  // zero padding: the stash row is dim_xyz_pad wide, the operand one fp16 k-step (16) granular
-            for (int k = p.dim_xyz; k < p.dim_xyz_pad; ++k) put(k, 0.f);
-            sx = nullptr;
-            for (int k = p.dim_xyz_pad; k < ((p.dim_xyz_pad + 15) & ~15); ++k) put(k, 0.f);
-          }
+          if (half == 1)  // zero padding up to the operand width (one fp16 k-step = 16 granular)
+            for (int k = p.dim_xyz; k < enc_w; ++k) put(k, 0.f);
         }
         // ---- per-ray direction term of layers_dir[0]: vb[ray][n] = (sum_k enc_dir(ray)[k] * W[n][H + k] + b[n]) / 16
         if (p.use_viewdirs) {
@@ -499,55 +424,21 @@ mlp_chain_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ bl
           }
         }
         tc_fence_before();
-        fence_proxy_async();  // E was written through the generic proxy; the MMAs read it via the async proxy
-        if (kTrain && tid == 0) bulk_wait_read();  // transpose tiles below overlap the staging tile
+        fence_proxy_async();  // E was written through the generic proxy; the MMAs / the bulk store read it via the async proxy
         epi_bar256();         // also publishes viewb
-        if (kTrain) {
-          if (p.dim_xyz_pad == 64) {
-            // this thread's row, channels [32*half, 32*half + 32): (hi + lo 2^-11) 16 is the value the forward contracts with
-            float x[32];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const uint4 h8 = *reinterpret_cast<const uint4*>(e_hi + (4 * half + q) * kSlabBytes + row * 16);
-              const uint4 l8 = *reinterpret_cast<const uint4*>(e_hi + (8 + 4 * half + q) * kSlabBytes + row * 16);
-              const uint32_t hh[4] = {h8.x, h8.y, h8.z, h8.w}, ll[4] = {l8.x, l8.y, l8.z, l8.w};
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                x[8 * q + 2 * i] = fmaf(f16_lo_to_f32(ll[i]), kLoInv, f16_lo_to_f32(hh[i])) * kActInv;
-                x[8 * q + 2 * i + 1] = fmaf(f16_hi_to_f32(ll[i]), kLoInv, f16_hi_to_f32(hh[i])) * kActInv;
-              }
-            }
-            store_tile_coalesced(tbuf, x, stash + (size_t)P * p.enc_cum[0] + (size_t)wrow0 * 64 + 32 * half, 64, lane,
-                                 rows_valid);
-          }
-          if (valid && p.use_viewdirs && half == 0) {
-            float4* sd = reinterpret_cast<float4*>(stash + (size_t)P * p.enc_cum[1] + (size_t)pt * p.dim_dir_pad);
-            const float4* se = reinterpret_cast<const float4*>(encd + ts.ray_slot * 32);
-            for (int k = 0; k < (p.dim_dir_pad >> 2); ++k) __stcs(sd + k, se[k]);
-          }
-          epi_bar256();  // the transpose tiles alias the staging tile the first layer's epilogue writes
-        }
+        if (kTrain && tid == 0)  // the encoding tile goes to the stash as it is: one bulk store
+          bulk_s2g(reinterpret_cast<uint8_t*>(stash + (size_t)P_pad * p.enc_cum[0]) + (size_t)ts.tile * tile_bytes(enc_w),
+                   e_hi, (uint32_t)tile_bytes(enc_w));
         mbar_arrive(&bar_a1[s]);
         mbar_arrive(&bar_a2[s]);
         return;
       }
 
-      if (kMode == 1 && e == 0) {
-        const float4 d4 = valid ? reinterpret_cast<const float4*>(raw)[pt] : make_float4(0.f, 0.f, 0.f, 0.f);
-        // this row's power-of-two scale: 2^(123 - e) with e the biased exponent of max |d_raw[row]| (1 for zero rows):
-        // the scaled row has max-abs in [2^-4, 2^-3)
-        const float m = fmaxf(fmaxf(fabsf(d4.x), fabsf(d4.y)), fmaxf(fabsf(d4.z), fabsf(d4.w)));
-        const uint32_t ex = (__float_as_uint(m) >> 23) & 0xFFu;
-        const bool scaled = ex >= 1u && ex <= 249u;
-        const float sc = scaled ? __uint_as_float((250u - ex) << 23) : 1.f;
-        ts.unscale = scaled ? __uint_as_float((ex + 4u) << 23) : 1.f;
-        ts.dr[0] = d4.x * sc; ts.dr[1] = d4.y * sc; ts.dr[2] = d4.z * sc; ts.dr[3] = d4.w * sc;
-      }
-
       // ================= one layer =================
-      const int t = kMode == 0 ? e - 1 : p.n_gemm - 1 - e;
+      const int64_t pt = ts.pt;
+      const bool valid = ts.valid;
+      const int t = e - 1;
       const GemmLayer& g = p.g[t];
-      const bool has_mma = kMode == 0 ? true : e >= 1;
       const bool has_next = e < nM;
       int hsel = -1;
       if (p.h[0].src == t) hsel = 0;
@@ -556,74 +447,53 @@ mlp_chain_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ bl
       const int hk = hsel >= 0 ? p.h[hsel].k : 0, hn = hsel >= 0 ? p.h[hsel].n_out : 0;
       const int hcol = hsel >= 0 ? p.h[hsel].out_col : 0;
       float hacc[4] = {0.f, 0.f, 0.f, 0.f};
-      const bool is_dir = kMode == 0 && p.use_viewdirs && t == p.n_gemm - 1;
-      constexpr bool train = kMode == 1 || kTrain;
-      // training side outputs / inputs of this layer
+      const bool is_dir = p.use_viewdirs && t == p.n_gemm - 1;
       uint32_t* mask_row = nullptr;
-      if (kMode == 0 ? kTrain : (g.relu != 0))
-        mask_row = reinterpret_cast<uint32_t*>(stash) + (size_t)P * (p.mask_base + g.mask_cum) + (size_t)pt * (g.n >> 5);
+      if (kTrain && valid)
+        mask_row = reinterpret_cast<uint32_t*>(stash) + (size_t)P_pad * (p.mask_base + g.mask_cum) + (size_t)pt * (g.n >> 5);
 
-      // dgrad: fetch this row's ReLU mask words now so that their latency hides behind the MMA wait
-      uint32_t mw[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};
-      if (kMode == 1 && g.relu) {
-        mw[0] = valid ? __ldg(mask_row + half) : 0u;                       // columns [32*half, +32)
-        mw[1] = (valid && g.n == 128) ? __ldg(mask_row + 2 + half) : 0u;     // columns [64 + 32*half, +32)
-      }
-      if (train) {  // the previous bulk store must have finished reading the staging tile; checked BEFORE the
-        if (tid == 0) bulk_wait_read();  // accumulator wait, so this barrier hides under the MMAs
-        epi_bar256();
-      }
-      if (has_mma) {
-        mbar_wait(&bar_acc[s], ts.acc_phase);
-        ts.acc_phase ^= 1;
-        tc_fence_after();
-      }
+      mbar_wait(&bar_acc[s], ts.acc_phase);
+      ts.acc_phase ^= 1;
+      tc_fence_after();
 
       {
         ChunkArgs ca;
-        ca.bias = (kMode == 0) ? (is_dir ? viewb + ts.ray_slot * 64 : s_bias + g.cum_n) : nullptr;
+        ca.bias = is_dir ? viewb + ts.ray_slot * 64 : s_bias + g.cum_n;
         ca.lb = g.relu ? 0.f : -3.4e38f;
         ca.hw = hw; ca.hk = hk;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) ca.hd[c] = ts.dr[(hcol + c) & 3];
         ca.has_next = has_next;
-        ca.row7 = row & 7;
-        ca.unscale = ts.unscale;
-        ca.stg_row = train ? staging + (size_t)row * g.n * 4 : nullptr;
+        ca.stash_hi = nullptr;
+        ca.stash_lo_off = tile_half_bytes(g.n);
+        if (kTrain)
+          ca.stash_hi = reinterpret_cast<uint8_t*>(stash + (size_t)P_pad * g.cum_n) + (size_t)ts.tile * tile_bytes(g.n) +
+                        tile_piece(row, 0, g.n);
         // column chunks of this thread: first [32*half, +32), second [64 + 32*half, +32) (128-wide layers only).
         // Both are pulled out of the accumulator up front; after the first chunk's A columns are stored the
         // next MMA may start its first four k-steps (bar_a1), the second chunk follows under that shadow.
         const int nch = g.n >> 6;  // 2 for 128-wide layers, 1 for 64-wide ones
         const int c0a = 32 * half, c0b = 64 + 32 * half;
         uint32_t v0[32], v1[32];
-        if (has_mma) {
-          tmem_ld32(t_acc + c0a, v0);
-          if (nch == 2) tmem_ld32(t_acc + c0b, v1);
-          tmem_wait_ld();
-        } else {
-#pragma unroll
-          for (int jj = 0; jj < 32; ++jj) v0[jj] = v1[jj] = 0u;
-        }
-        ca.mword_in = mw[0];
-        ca.mword_out = (kMode == 0 && mask_row && valid) ? mask_row + (c0a >> 5) : nullptr;
+        tmem_ld32(t_acc + c0a, v0);
+        if (nch == 2) tmem_ld32(t_acc + c0b, v1);
+        tmem_wait_ld();
+        ca.mword_out = mask_row ? mask_row + (c0a >> 5) : nullptr;
         ca.tmem_hi = t_ahi + c0a / 2;  // two fp16 per tensor-memory column
         ca.tmem_lo = t_alo + c0a / 2;
-        epilogue_chunk_dispatch<kMode, train>(hn, v0, c0a, ca, hacc);
+        epilogue_chunk_dispatch<kTrain>(hn, v0, c0a, ca, hacc);
         if (has_next) {
           tmem_wait_st();
           tc_fence_before();
           mbar_arrive(&bar_a1[s]);
         }
         if (nch == 2) {
-          ca.mword_in = mw[1];
-          ca.mword_out = (kMode == 0 && mask_row && valid) ? mask_row + (c0b >> 5) : nullptr;
+          ca.mword_out = mask_row ? mask_row + (c0b >> 5) : nullptr;
           ca.tmem_hi = t_ahi + c0b / 2;
           ca.tmem_lo = t_alo + c0b / 2;
-          epilogue_chunk_dispatch<kMode, train>(hn, v1, c0b, ca, hacc);
+          epilogue_chunk_dispatch<kTrain>(hn, v1, c0b, ca, hacc);
         }
       }
 
-      if (kMode == 0 && hsel >= 0 && half == 1)
+      if (hsel >= 0 && half == 1)
         *reinterpret_cast<float4*>(hpart + (hsel * 128 + row) * 4) = make_float4(hacc[0], hacc[1], hacc[2], hacc[3]);
       if (has_next) {
         tmem_wait_st();
@@ -632,14 +502,8 @@ mlp_chain_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ bl
       } else {
         tc_fence_before();
       }
-      if (train) fence_proxy_async();  // staging tile written through the generic proxy, read by the bulk copy
-      if (train || (kMode == 0 && hsel >= 0)) epi_bar256();  // staging tile complete / head partials in hpart
-      if (train && tid == 0) {
-        const int64_t rows_tile = P - p0 < kTileRows ? P - p0 : kTileRows;
-        float* dst = (kMode == 0 ? stash : gstash) + (size_t)P * g.cum_n + (size_t)p0 * g.n;
-        bulk_s2g(dst, staging, (uint32_t)(rows_tile * g.n * 4));
-      }
-      if (kMode == 0 && hsel >= 0) {
+      if (hsel >= 0) {
+        epi_bar256();  // head partials in hpart
         if (half == 0 && valid) {
           const float4 o = *reinterpret_cast<const float4*>(hpart + (hsel * 128 + row) * 4);
           const float tot[4] = {hacc[0] + o.x + s_headb[hsel * 4 + 0], hacc[1] + o.y + s_headb[hsel * 4 + 1],
@@ -664,7 +528,7 @@ mlp_chain_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ bl
   if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols));
 }
 
-static int tc_supported(const Plan& p, int n_samples, bool training, const char* what) {
+int tc_supported(const Plan& p, int n_samples, const char* what) {
   if (p.hidden != 128) {
     set_error("%s impl=1 (tcgen05): hidden_size %d not supported (128 only); use impl=0", what, p.hidden);
     return NERFB200_ERR_UNSUPPORTED;
@@ -677,7 +541,7 @@ static int tc_supported(const Plan& p, int n_samples, bool training, const char*
     set_error("%s impl=1 (tcgen05): fewer than 16 samples per ray not supported; use impl=0", what);
     return NERFB200_ERR_UNSUPPORTED;
   }
-  if (smem_map(p, training).n_stages < 2) {
+  if (smem_map(p).n_stages < 2) {
     set_error("%s impl=1 (tcgen05): network too deep for the shared-memory budget (%d layers); use impl=0", what,
               p.n_gemm);
     return NERFB200_ERR_UNSUPPORTED;
@@ -685,9 +549,9 @@ static int tc_supported(const Plan& p, int n_samples, bool training, const char*
   return NERFB200_OK;
 }
 
-template <int kMode, bool kTrain>
-static int launch_chain(const Plan& p, const float* blob, const float* rays, int ray_stride, const float* z, int64_t P,
-                        int n_samples, float* raw, float* stash, float* gstash, cudaStream_t s, const char* what) {
+template <bool kTrain>
+static int launch_fwd(const Plan& p, const float* blob, const float* rays, int ray_stride, const float* z, int64_t P,
+                      int n_samples, float* raw, float* stash, cudaStream_t s, const char* what) {
   const int64_t tiles = (P + kTileRows - 1) / kTileRows;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -695,32 +559,24 @@ static int launch_chain(const Plan& p, const float* blob, const float* rays, int
   // two tiles in flight per CTA: do not spread fewer than 2 tiles per CTA over more CTAs than needed
   int64_t want = (tiles + 1) / 2;
   const int grid = (int)(want < sms ? (want < 1 ? 1 : want) : sms);
-  const size_t bytes = (size_t)smem_map(p, kTrain).total + 1024;
-  auto kern = mlp_chain_tc_kernel<kMode, kTrain>;
+  const size_t bytes = (size_t)smem_map(p).total + 1024;
+  auto kern = mlp_fwd_tc_kernel<kTrain>;
   int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes), what);
   if (rc) return rc;
-  kern<<<grid, kThreadsTc, bytes, s>>>(p, blob, rays, ray_stride, z, P, n_samples, tiles, raw, stash, gstash);
+  kern<<<grid, kThreadsTc, bytes, s>>>(p, blob, rays, ray_stride, z, P, n_samples, tiles, raw, stash);
   count_launch();
   return check_cuda(cudaGetLastError(), what);
 }
 
 int launch_mlp_fwd_tc(const Plan& p, const float* blob, const float* rays, int ray_stride, const float* z,
                       int64_t n_rays, int n_samples, float* raw, float* stash, cudaStream_t s) {
-  int rc = tc_supported(p, n_samples, stash != nullptr, "mlp_fwd");
+  int rc = tc_supported(p, n_samples, "mlp_fwd");
   if (rc) return rc;
   if (stash)
-    return launch_chain<0, true>(p, blob, rays, ray_stride, z, n_rays * n_samples, n_samples, raw, stash, nullptr, s,
-                                 "mlp_fwd_tc launch");
-  return launch_chain<0, false>(p, blob, rays, ray_stride, z, n_rays * n_samples, n_samples, raw, nullptr, nullptr, s,
-                                "mlp_fwd_tc launch");
-}
-
-int launch_dgrad_tc(const Plan& p, const float* blob, const float* d_raw, const float* stash, float* gstash, int64_t P,
-                    cudaStream_t s) {
-  int rc = tc_supported(p, 0, true, "dgrad");
-  if (rc) return rc;
-  return launch_chain<1, true>(p, blob, nullptr, 0, nullptr, P, 1, const_cast<float*>(d_raw),
-                               const_cast<float*>(stash), gstash, s, "dgrad_tc launch");
+    return launch_fwd<true>(p, blob, rays, ray_stride, z, n_rays * n_samples, n_samples, raw, stash, s,
+                            "mlp_fwd_tc launch");
+  return launch_fwd<false>(p, blob, rays, ray_stride, z, n_rays * n_samples, n_samples, raw, nullptr, s,
+                           "mlp_fwd_tc launch");
 }
 
 }  // namespace nerfb200

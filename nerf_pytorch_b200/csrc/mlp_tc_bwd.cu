@@ -1,346 +1,743 @@
-// mlp_tc_bwd.cu -- tcgen05 weight-gradient kernel:  dW[n][k] = sum_p dY[p][n] * X[p][k]   (3xTF32)
+// mlp_tc_bwd.cu -- tcgen05 backward of FlexibleNeRFModel (nerf/models.py:233-256, autograd of train_nerf.py:259) for
+// hidden_size 128: the data-gradient chain AND every weight gradient of a 128-point tile in ONE kernel, so that the
+// per-layer pre-activation gradients G_t never leave the SM (no gradient stash in HBM).
 //
-// One CTA = one (layer, row-block, column-block) item of wgrad_items.cuh -- the 1..4-row heads included -- over a
-// contiguous range of points.  The reduction runs over POINTS while the stash rows dY[p][:] / X[p][:] are
-// feature-contiguous, so both operands are transposed on chip, 32 points per pipeline stage:
-//   copy warp    both stashes are dense row-major arrays, so the 32 rows of a stage are ONE contiguous block per
-//                operand: one cp.async.bulk each into a 4-deep ring of raw tiles (mbarrier complete_tx).  128 KB
-//                per SM stay in flight, which is what keeps HBM busy (register prefetch could not).
-//   A = dY^T     (M = 128 output features) lives in TENSOR MEMORY (lane = feature, column = point): every thread
-//                reads ITS feature of the 32 raw rows (conflict-free 4-byte loads: the stash chunk swizzle is a
-//                permutation inside each 128-byte segment), splits hi/lo and writes both with two tcgen05.st.
-//   B = X^T      (N = 128|64|48.. input features) goes to shared memory: float4 reads of 4 features x 4 points,
-//                4x4 register transpose, hi/lo split, 64 contiguous bytes per operand into the UMMA canonical
-//                K-major no-swizzle layout (slab = [feature][4 points], core matrices padded to 144 B apart so the
-//                stores are bank-conflict free).
-//   Two transposer groups (8 warps each) alternate stages: the chain wait -> read -> split -> store -> fence ->
-//   arrive is latency-bound for one warp, so two stages are always being transposed.
-//   MMA warp     three tcgen05.mma.kind::tf32 per 8 points (hi*hi, lo*hi, hi*lo; A from tensor memory) into a
-//                128 x N fp32 accumulator in tensor memory that lives for the whole point range; at the end the
-//                A warps drain it with tcgen05.ld and atomically add into the flat gradient.
-// Per point and item the kernel reads (n + k) * 4 bytes from HBM exactly once; it runs at ~80 % of the measured
-// HBM bandwidth.
+//   chain  : G_t = (G_{t+1} W_{t+1}[:, :hidden] + d_raw W_head) (.) relu'(layer t)          (M = points, K = features)
+//   wgrad  : dW_t[n][k] += sum_p G_t[p][n] X_{t-1}[p][k]                                    (M = features n, K = points)
+// Both are 3-term split-precision products on tcgen05.mma.kind::f16 (tc_common.cuh split_f16x2).  The trick that
+// makes the fusion cheap is the operand tile (tc_common.cuh "Operand tiles"): G_t is split into fp16 hi / lo ONCE in
+// the epilogue registers; the same registers go to tensor memory (A operand of the chain, K-major) and to a
+// shared-memory tile whose MN-major view is the A operand of the weight-gradient MMAs; the forward stashed every
+// layer's activation X_t as the same kind of tile, so the B operand of the weight-gradient MMAs is a plain bulk copy
+// from HBM.  Nothing is transposed on the CUDA cores.
+//
+// Precision: the whole tile runs in ONE power-of-two scale (max |d_raw| of the tile -> [4, 8)): the reduction of a
+// weight gradient runs over points, so rows must share a scale, and rows that are tiny next to the tile's largest
+// contribute below fp32 resolution to dW anyway.  The residual products carry a factor 2^11 (lo = (x - hi) 2^11 on
+// both sides); they are accumulated first and folded in by the scale-input-d form of the first hi*hi MMA
+// (D = A*B + D * 2^-11), so a weight gradient needs ONE accumulator and no pre-scaled operand copies.
+//
+// Persistent kernel, one CTA per SM, 352 threads:
+//   warps 0-7  epilogue (thread = (point row, column half)): per layer  part A: accumulator -> + head term, ReLU mask,
+//              split -> tensor memory (chain A operand);  drain the previous layer's weight-gradient accumulators
+//              (tcgen05.ld -> unscale -> swizzled staging tile -> cp.reduce.async.bulk .add.f32 into the L2-resident
+//              gradient blob);  part B: the held hi / lo registers -> shared-memory G tile.
+//   warp 8     MMA issuer: chain MMA of the layer (A from tensor memory, B = weights from the ring), then the layer's
+//              weight-gradient jobs (A = G tile, B = activation tile, both MN-major from shared memory) and the
+//              16-column ray-indicator job that yields the bias gradients and the per-ray sums of layers_dir[0].
+//   warp 9     weight producer (cp.async.bulk ring, one k-step per stage)
+//   warp 10    activation-tile producer (hi block / lo block of one job at a time)
+// Tensor memory: [0,128) chain accumulator, [128,256) chain A operand (hi | lo), [256,384) job slot 0,
+// [384,400) indicator sums, [400,464) job slot 1 (jobs at most 64 wide).
 #include "common.cuh"
 #include "tc_common.cuh"
-#include "wgrad_items.cuh"
 
 namespace nerfb200 {
 
-namespace tcw {
-constexpr int kThreadsW = 576;               // warps 0-3/8-11: A, 4-7/12-15: B (even/odd stages), 16: MMA + TMEM alloc, 17: copies
-constexpr int kWarpMma = 16;
-constexpr int kStagePts = 32;                // points per pipeline stage = 4 MMA k-groups
-// Both rings have an EVEN number of slots, so a slot always belongs to the same transposer group: a parity wait
-// is only safe if the waiting thread itself consumed the slot's previous phase.
-constexpr int kRawStages = 4;                // ring of raw row blocks filled by the copy engine
-constexpr int kOpStages = 2;                 // ring of transposed operands (B in shared memory, A in tensor memory)
-constexpr int kSboW = 144;                   // 8-feature core matrices 128 B + 16 B pad apart
-constexpr int kSlabW = 16 * kSboW;           // 128 features x 4 points (one K-major slab), padded
-constexpr int kOpBytes = (kStagePts / 4) * kSlabW;  // one B tile (hi or lo): 8 slabs = 18 KB
-constexpr int kStageBytesW = 2 * kOpBytes;   // B_hi | B_lo
-constexpr int kRawHalf = kStagePts * 512;    // raw copy of 32 rows of <= 128 features
-constexpr int kRawBytes = 2 * kRawHalf;      // dY rows | X rows
-constexpr uint32_t kTmemColsW = 512;
-constexpr uint32_t kColAccW = 0;             // accumulator: 128 columns
-constexpr uint32_t kColA = 128;              // per operand stage 64 columns: A_hi (32 points) | A_lo (32 points)
-}  // namespace tcw
+namespace tcb {
+constexpr int kThreadsB = 352;
+constexpr int kEpi = 256;
+constexpr int kWStage = 96 * 128;                 // one k-step of a 128-wide layer: 3 copies x 2 slabs x 128 x 16 B
+constexpr int kMaxWStages = 6;
+constexpr int kGBytes = 65536;                    // G tile: hi block 32 KB, lo block 32 KB (128 features)
+constexpr int kXBytes = 65536;                    // activation tile of the running job
+constexpr int kStgBytes = 8192;                   // staging chunk: 128 rows x 16 fp32; two per column half (double buffer)
+constexpr int kIndBytes = 4096;                   // ray-indicator tile: 128 points x 16 "features" (hi only)
+constexpr int kMaxRays = 10;
+constexpr uint32_t kTmemColsB = 512;
+constexpr uint32_t kColAcc = 0, kColAhi = 128, kColAlo = 192, kColSlot0 = 256, kColInd = 384, kColSlot1 = 400;
+constexpr int kSmemLimitB = 232448 - 1024;
 
-using namespace tc;
-using namespace tcw;
-
-__device__ __forceinline__ void split_store(uint8_t* hi_base, uint8_t* lo_base, int off, float4 v) {
-  uint4 h;
-  h.x = tf32_hi(v.x); h.y = tf32_hi(v.y); h.z = tf32_hi(v.z); h.w = tf32_hi(v.w);
-  float4 l = make_float4(v.x - __uint_as_float(h.x), v.y - __uint_as_float(h.y), v.z - __uint_as_float(h.z),
-                         v.w - __uint_as_float(h.w));
-  *reinterpret_cast<uint4*>(hi_base + off) = h;
-  *reinterpret_cast<float4*>(lo_base + off) = l;
+struct SmemMapB {
+  int g, x, stg, ind, headw, bgrad, dgrad, encd, misc, bars, ring, total, n_stages;
+};
+__host__ __device__ inline SmemMapB smem_map_b(const Plan& p) {
+  SmemMapB m;
+  int off = 0;
+  m.g = off;      off += kGBytes;
+  m.x = off;      off += kXBytes;
+  m.stg = off;    off += 4 * kStgBytes;
+  m.ind = off;    off += kIndBytes;
+  m.headw = off;  off += (4 * 128 + 3 * 64 + 16) * 4;
+  m.bgrad = off;  off += (p.enc_cum[0] + 8) * 4;   // bias gradients of every gemm layer + the heads' (8)
+  m.dgrad = off;  off += 64 * 32 * 4;              // direction-encoding part of dW(layers_dir[0]): [n][e]
+  m.encd = off;   off += kMaxRays * 32 * 4;
+  m.misc = off;   off += 64;
+  m.bars = off;   off += 256;
+  off = (off + 1023) & ~1023;
+  m.ring = off;
+  int ns = (kSmemLimitB - off) / kWStage;
+  if (ns > kMaxWStages) ns = kMaxWStages;
+  m.n_stages = ns;
+  m.total = off + (ns > 0 ? ns : 0) * kWStage;
+  return m;
 }
 
-__global__ void __launch_bounds__(kThreadsW, 1)
-mlp_wgrad_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ stash, const float* __restrict__ gstash,
-                    const float* __restrict__ d_raw, int64_t P, float* __restrict__ flat_grad,
-                    const __grid_constant__ WgGrid grid) {
+// One weight-gradient job: accumulator[n][k] = sum_p G[p][n] * B[p][k] over the tile's 128 points.
+struct BwdJob {
+  int src_enc;   // B tile: 1 = the xyz-encoding tile, 0 = the stashed output of gemm layer `src`
+  int src;
+  int n_b;       // columns = width of the B tile (multiple of 16)
+  int col;       // tensor-memory column of the accumulator
+  int row0, nrows;  // accumulator rows that carry gradients
+  int gb_off;    // float offset of this job's block in the gradient blob: [n_b / 16 chunks][128 rows][16]
+  int dst_head;  // -1: rows are output features of gemm layer `dst`; else head index, rows row0.. are its outputs
+  int dst;       // gemm index
+  int dst_col0;  // first input column of the destination weight this block covers
+  int ncols;     // real columns
+  int reuse_slot0;  // must wait until the first job of the event has been drained
+};
+constexpr int kMaxJobs = 3;
+
+// jobs of event e (layer t = n_gemm - 1 - e); returns their number.  gb offsets are cumulative over the events.
+__host__ __device__ inline int bwd_jobs(const Plan& p, int e, BwdJob* out, int* gb_total = nullptr) {
+  int gb = 0, n_out = 0;
+  for (int ev = 0; ev <= (gb_total ? p.n_gemm - 1 : e); ++ev) {
+    const int t = p.n_gemm - 1 - ev;
+    const GemmLayer& g = p.g[t];
+    int n = 0;
+    BwdJob jb[kMaxJobs];
+    auto add = [&](int src_enc, int src, int n_b, int col, int row0, int nrows, int dst_head, int dst, int dst_col0,
+                   int ncols, int reuse) {
+      BwdJob& j = jb[n++];
+      j.src_enc = src_enc; j.src = src; j.n_b = n_b; j.col = col; j.row0 = row0; j.nrows = nrows;
+      j.gb_off = gb; j.dst_head = dst_head; j.dst = dst; j.dst_col0 = dst_col0; j.ncols = ncols; j.reuse_slot0 = reuse;
+      gb += (n_b / 16) * 128 * 16;
+    };
+    if (g.k_h > 0) add(0, g.src, g.k_h, (int)kColSlot0, 0, g.n, -1, t, 0, g.k_h, 0);
+    if (g.k_enc > 0 && g.enc_sel == 0)
+      add(1, 0, p.enc_tile_w, g.k_h > 0 ? (int)kColSlot1 : (int)kColSlot0, 0, g.n, -1, t, g.k_h, g.enc_real, 0);
+    if (p.use_viewdirs && t == p.n_gemm - 1) {
+      // the heads ride on the spare rows of the 64-wide layers_dir[0] tile: rows 64..66 = d_rgb, row 67 = d_sigma
+      add(0, t, g.n, (int)kColSlot1, 64, 3, 1, t, 0, p.h[1].k, 0);                            // fc_rgb reads this layer's output
+      add(0, p.h[0].src, p.g[p.h[0].src].n, (int)kColSlot0, 67, 1, 0, t, 0, p.h[0].k, 1);     // fc_alpha reads the trunk output
+    }
+    if (ev == e && out)
+      for (int i = 0; i < n; ++i) out[i] = jb[i];
+    if (ev == e) n_out = n;
+  }
+  if (gb_total) *gb_total = gb;
+  return n_out;
+}
+
+// the job table of a network, built on the host once per launch and passed by value (no per-thread enumeration)
+struct BwdPlan {
+  int n_jobs[kMaxGemm];
+  BwdJob jobs[kMaxGemm][kMaxJobs];
+  int gb_total;
+};
+inline BwdPlan make_bwd_plan(const Plan& p) {
+  BwdPlan bp;
+  for (int e = 0; e < p.n_gemm; ++e) bp.n_jobs[e] = bwd_jobs(p, e, bp.jobs[e]);
+  bwd_jobs(p, 0, nullptr, &bp.gb_total);
+  return bp;
+}
+
+}  // namespace tcb
+
+using namespace tc;
+using namespace tcb;
+
+// Development build only (make EXTRA=-DNERFB200_PROF): CTA 0 adds up the cycles its roles spend in each phase.
+#ifdef NERFB200_PROF
+__device__ unsigned long long g_prof[32];
+#define PROF_T0() const long long _pt0 = clock64()
+#define PROF_ADD(i) do { if (blockIdx.x == 0) g_prof[i] += (unsigned long long)(clock64() - _pt0); } while (0)
+#define PROF_SCOPE(i, stmt) do { const long long _ps = clock64(); stmt; if (blockIdx.x == 0) g_prof[i] += (unsigned long long)(clock64() - _ps); } while (0)
+#else
+#define PROF_SCOPE(i, stmt) do { stmt; } while (0)
+#endif
+
+__device__ __forceinline__ void bar_half(int half) {  // the 128 threads of one column half
+  asm volatile("bar.sync %0, 128;" ::"r"(2 + half) : "memory");
+}
+
+__global__ void __launch_bounds__(kThreadsB, 1)
+mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob, const float* __restrict__ rays,
+                  int ray_stride, const float* __restrict__ d_raw, const float* __restrict__ stash, int64_t P, int S,
+                  int64_t n_tiles, float* __restrict__ gblob, float* __restrict__ flat_grad,
+                  const __grid_constant__ BwdPlan bp) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* raw = sm + kOpStages * kStageBytesW;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(raw + kRawStages * kRawBytes);
-  uint64_t* raw_full = bars;                          // copy engine -> transposers (transaction bytes)
-  uint64_t* raw_empty = raw_full + kRawStages;        // 8 transposer warps -> copy warp
-  uint64_t* op_full = raw_empty + kRawStages;         // 256 transposer threads -> MMA warp
-  uint64_t* op_empty = op_full + kOpStages;           // tcgen05.commit -> transposers
-  uint64_t* bar_done = op_empty + kOpStages;
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_done + 1);
+  const SmemMapB mp = smem_map_b(p);
+  uint8_t* sG = sm + mp.g;
+  uint8_t* sX = sm + mp.x;
+  uint8_t* sInd = sm + mp.ind;
+  float* s_headw = reinterpret_cast<float*>(sm + mp.headw);
+  float* s_bgrad = reinterpret_cast<float*>(sm + mp.bgrad);
+  float* s_dgrad = reinterpret_cast<float*>(sm + mp.dgrad);
+  float* s_encd = reinterpret_cast<float*>(sm + mp.encd);
+  uint32_t* s_max = reinterpret_cast<uint32_t*>(sm + mp.misc);      // [2]: tile max of |d_raw| (alternating tiles)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + mp.bars);
+  uint64_t* w_full = bars;                      // [kMaxWStages]
+  uint64_t* w_empty = bars + kMaxWStages;       // [kMaxWStages]
+  uint64_t* bar_a = bars + 2 * kMaxWStages;     // chain A operand written (and chain accumulator drained)
+  uint64_t* bar_acc = bar_a + 1;                // chain MMA complete
+  uint64_t* bar_g = bar_acc + 1;                // G tile (+ indicator tile) written
+  uint64_t* xh_full = bar_g + 1;
+  uint64_t* xl_full = xh_full + 1;
+  uint64_t* xh_free = xl_full + 1;
+  uint64_t* xl_free = xh_free + 1;
+  uint64_t* job_done = xl_free + 1;             // [kMaxJobs]: job i of the running event complete
+  uint64_t* slot0_free = job_done + kMaxJobs;   // first job of a three-job event drained
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(slot0_free + 1);
+  const uint32_t n_stages = (uint32_t)mp.n_stages;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  int item = 0;
-  while (item + 1 < grid.n_items && (int)blockIdx.x >= grid.start[item + 1]) ++item;
-  const int part = (int)blockIdx.x - grid.start[item], parts = grid.start[item + 1] - grid.start[item];
-  const WgItem it = wg_decode(p, item);
-  // operand sources.  gemm items: A rows = dY_t (gstash), B rows = the producing layer's output or the stashed
-  // encoding.  Head items (fc_alpha / fc_rgb / fc_out): A rows = d_raw[p][0..3] restricted to the head's columns
-  // (<= 4 live rows of the 128-row tile), B rows = the output of the layer the head reads.
-  const bool head = it.kind == 2;
-  const GemmLayer& g = p.g[head ? p.h[it.t].src : it.t];
-  const int hcol0 = head ? p.h[it.t].out_col : 0, hcols = head ? p.h[it.t].n_out : 0;
-  // both sources are dense row-major [P][width] arrays, so 32 consecutive points are ONE contiguous block
-  int wa, wb;  // floats per dY row / per X row
-  wg_row_widths(p, it, &wa, &wb);
-  const float* src_a = head ? d_raw : gstash + (size_t)P * g.cum_n;
-  const float* src_b = head ? stash + (size_t)P * g.cum_n
-                            : (it.kind == 0 ? stash + (size_t)P * p.g[g.src].cum_n
-                                            : stash + (size_t)P * p.enc_cum[g.enc_sel]);
-
-  // contiguous point range of this CTA, in units of one stage
-  const int64_t stages_total = (P + kStagePts - 1) / kStagePts;
-  const int64_t per = (stages_total + parts - 1) / parts;
-  int64_t pt_begin = (int64_t)part * per * kStagePts;
-  int64_t pt_end = pt_begin + per * kStagePts;
-  if (pt_begin > P) pt_begin = P;
-  if (pt_end > P) pt_end = P;
-  if (pt_begin >= pt_end) return;
-  const int64_t n_stage = (pt_end - pt_begin + kStagePts - 1) / kStagePts;
+  const int64_t P_pad = n_tiles * kTileRows;
+  const int E = p.n_gemm;
+  const int hw1 = p.h[0].n_out * p.h[0].k;
+  const int hw2 = p.n_head > 1 ? p.h[1].n_out * p.h[1].k : 0;
 
   if (tid == 0) {
-    for (int i = 0; i < kRawStages; ++i) {
-      mbar_init(&raw_full[i], 1);
-      mbar_init(&raw_empty[i], 8);
+    for (int i = 0; i < kMaxWStages; ++i) {
+      mbar_init(&w_full[i], 1);
+      mbar_init(&w_empty[i], 1);
     }
-    for (int i = 0; i < kOpStages; ++i) {
-      mbar_init(&op_full[i], 256);
-      mbar_init(&op_empty[i], 1);
-    }
-    mbar_init(bar_done, 1);
+    mbar_init(bar_a, kEpi);
+    mbar_init(bar_acc, 1);
+    mbar_init(bar_g, kEpi);
+    mbar_init(xh_full, 1);
+    mbar_init(xl_full, 1);
+    mbar_init(xh_free, 1);
+    mbar_init(xl_free, 1);
+    for (int i = 0; i < kMaxJobs; ++i) mbar_init(&job_done[i], 1);
+    mbar_init(slot0_free, kEpi);
     fence_barrier_init();
+    s_max[0] = s_max[1] = 0u;
   }
-  if (warp == kWarpMma) {
+  if (warp == 8) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)),
-                 "r"(kTmemColsW));
+                 "r"(kTmemColsB));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
-  // zero the B tiles once: feature rows outside the item stay zero for the whole kernel
-  for (int i = tid; i < kOpStages * kStageBytesW / 16; i += kThreadsW)
-    reinterpret_cast<uint4*>(sm)[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = tid; i < hw1; i += kThreadsB) s_headw[i] = blob[p.h[0].w_off + i];
+  for (int i = tid; i < hw2; i += kThreadsB) s_headw[hw1 + i] = blob[p.h[1].w_off + i];
+  for (int i = tid; i < p.enc_cum[0] + 8; i += kThreadsB) s_bgrad[i] = 0.f;
+  for (int i = tid; i < 64 * 32; i += kThreadsB) s_dgrad[i] = 0.f;
+  for (int i = tid; i < kMaxRays * 32; i += kThreadsB) s_encd[i] = 0.f;
+  for (int i = tid; i < kGBytes / 16; i += kThreadsB) reinterpret_cast<uint4*>(sG)[i] = make_uint4(0u, 0u, 0u, 0u);
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *s_tmem;
 
-  const int n_mma = it.kblk;  // accumulator columns (multiple of 16)
-  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int my_tiles = (n_tiles > blockIdx.x) ? (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
 
-  // two transposer groups alternate stages (group 0: warps 0-7, group 1: warps 8-15): the per-stage chain
-  // wait -> shared-memory reads -> split -> tcgen05.st / st.shared -> fence -> arrive is latency-bound for one
-  // warp, so two stages are kept in flight
-  const int grp = warp >> 3, wg = warp & 7;
-  if (warp < kWarpMma && wg < 4) {
-    // ===================== A: raw dY rows -> tensor memory (lane = feature, column = point) =====================
-    const int n = tid & 127;
-    const bool on_n = head ? (n >= hcol0 && n < hcol0 + hcols) : (n < it.nblk && n < wa);
-    const uint32_t lane_base = ((uint32_t)(wg * 32)) << 16;
-    const int row_b = wa * 4;
-    float bsum = 0.f;
-    for (int64_t s = grp; s < n_stage; s += 2) {
-      const uint32_t rs = (uint32_t)(s % kRawStages), rph = (uint32_t)(s / kRawStages) & 1u;
-      const uint32_t os = (uint32_t)(s % kOpStages), oph = (uint32_t)(s / kOpStages) & 1u;
-      const int rows = (int)min((int64_t)kStagePts, pt_end - (pt_begin + s * kStagePts));
-      uint32_t hi[32], lo[32];
-      mbar_wait(&raw_full[rs], rph);
-      if (on_n) {
-        const uint8_t* ar = raw + rs * kRawBytes + (n & 3) * 4;
-        // head rows are plain (feature n = column n of d_raw); stash rows are chunk-swizzled by (point & 7), and
-        // every stage starts at a multiple of 32 points
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int chunk = head ? 0 : ((n >> 2) ^ (j & 7));
-          float a = *reinterpret_cast<const float*>(ar + j * row_b + chunk * 16);
-          a = j < rows ? a : 0.f;
-          hi[j] = tf32_hi(a);
-          lo[j] = __float_as_uint(a - __uint_as_float(hi[j]));
-          bsum += a;
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) hi[j] = lo[j] = 0u;
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&raw_empty[rs]);
-      mbar_wait(&op_empty[os], oph ^ 1);
-      __syncwarp();  // (the spin loops above may leave the warp diverged; tcgen05.st is .sync.aligned)
-      tc_fence_after();
-      tmem_st32(tmem + lane_base + kColA + 64 * os, hi);
-      tmem_st32(tmem + lane_base + kColA + 64 * os + 32, lo);
-      tmem_wait_st();
-      tc_fence_before();
-      mbar_arrive(&op_full[os]);
-    }
-    if (it.bias && on_n) {
-      float* gb = head ? flat_grad + p.h[it.t].flat_b + (n - hcol0) : flat_grad + g.flat_b + it.n0 + n;
-      atomicAdd(gb, bsum);
-    }
-    // ===================== drain the accumulator (TMEM lane = output row n) =====================
-    mbar_wait(bar_done, 0);
-    __syncwarp();
-    tc_fence_after();
-    const int in_real = head ? p.h[it.t].k : g.k_h + g.enc_real;
-    const int coff = head ? 0 : (it.kind == 0 ? it.k0 : g.k_h);
-    const int kreal = head ? p.h[it.t].k : (it.kind == 0 ? it.kblk : g.enc_real);
-    float* dst = head ? flat_grad + p.h[it.t].flat_w + (size_t)(n - hcol0) * in_real
-                      : flat_grad + g.flat_w + (size_t)(it.n0 + n) * in_real + coff;
-    for (int c0 = 32 * grp; c0 < n_mma; c0 += 64) {  // the two groups share the drain
-      uint32_t v[32];
-      if (n_mma - c0 >= 32) {
-        tmem_ld32(tmem + lane_base + kColAccW + c0, v);
-      } else {  // 16 remaining columns (N = 48): read them with two x8 loads
-#pragma unroll
-        for (int h8 = 0; h8 < 2; ++h8) {
-          asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
-                       : "=r"(v[8 * h8 + 0]), "=r"(v[8 * h8 + 1]), "=r"(v[8 * h8 + 2]), "=r"(v[8 * h8 + 3]),
-                         "=r"(v[8 * h8 + 4]), "=r"(v[8 * h8 + 5]), "=r"(v[8 * h8 + 6]), "=r"(v[8 * h8 + 7])
-                       : "r"(tmem + lane_base + kColAccW + c0 + 8 * h8)
-                       : "memory");
-        }
-#pragma unroll
-        for (int j = 16; j < 32; ++j) v[j] = 0u;
-      }
-      tmem_wait_ld();
-      if (on_n) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (c0 + j < kreal) atomicAdd(dst + c0 + j, __uint_as_float(v[j]));
-      }
-    }
-    tc_fence_before();
-  } else if (warp < kWarpMma) {
-    // ===================== B: raw X rows -> K-major hi/lo slabs.  lane = 4-feature chunk, warp = point quad =====
-    const int c = lane;               // features 4c .. 4c+3
-    const int quad0 = warp & 3;       // this thread transposes quads quad0 and quad0 + 4 of every stage
-    const bool on = 4 * c < it.kblk && 4 * c < wb;
-    const bool swz = head || it.kind == 0;  // layer outputs are chunk-swizzled, the stashed encodings are plain
-    const int row_b = wb * 4;
-    for (int64_t s = grp; s < n_stage; s += 2) {
-      const uint32_t rs = (uint32_t)(s % kRawStages), rph = (uint32_t)(s / kRawStages) & 1u;
-      const uint32_t os = (uint32_t)(s % kOpStages), oph = (uint32_t)(s / kOpStages) & 1u;
-      const int rows = (int)min((int64_t)kStagePts, pt_end - (pt_begin + s * kStagePts));
-      float4 v[8];
-      mbar_wait(&raw_full[rs], rph);
-      if (on) {
-        const uint8_t* br = raw + rs * kRawBytes + kRawHalf;
-#pragma unroll
-        for (int h = 0; h < 2; ++h)
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int j = 4 * (quad0 + 4 * h) + i;
-            const int cc = swz ? (c ^ (j & 7)) : c;
-            const float4 x = *reinterpret_cast<const float4*>(br + j * row_b + cc * 16);
-            v[4 * h + i] = j < rows ? x : zero4;
+  if (warp == 9) {
+    // ===================== weight producer: the chain MMA of event e streams layer t's transposed copies ============
+    if (lane == 0) {
+      Pipe pp;
+      const uint64_t pol = l2_policy_evict_last();
+      for (int it = 0; it < my_tiles; ++it)
+        for (int e = 0; e + 1 < E; ++e) {
+          const GemmLayer& g = p.g[E - 1 - e];
+          const uint8_t* src = reinterpret_cast<const uint8_t*>(blob + g.tcd_off);
+          const uint32_t kbytes = 96u * (uint32_t)g.k_h;
+          for (int ks = 0; ks < (g.n >> 4); ++ks) {
+            PROF_SCOPE(18, mbar_wait(&w_empty[pp.stage], pp.phase ^ 1));
+            mbar_arrive_expect_tx(&w_full[pp.stage], kbytes);
+            bulk_g2s_hint(sm + mp.ring + pp.stage * kWStage, src + (size_t)ks * kbytes, kbytes, &w_full[pp.stage], pol);
+            pp.advance(n_stages);
           }
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&raw_empty[rs]);
-      mbar_wait(&op_empty[os], oph ^ 1);
-      if (on) {
-        uint8_t* hi_b = sm + os * kStageBytesW;
-        uint8_t* lo_b = hi_b + kOpBytes;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const float4 r0 = v[4 * h + 0], r1 = v[4 * h + 1], r2 = v[4 * h + 2], r3 = v[4 * h + 3];
-          // slab (quad) -> [feature/8][feature%8][4 points]; this thread owns 4 consecutive features = 64 B
-          const int off = (quad0 + 4 * h) * kSlabW + (c >> 1) * kSboW + (c & 1) * 64;
-          split_store(hi_b, lo_b, off + 0, make_float4(r0.x, r1.x, r2.x, r3.x));
-          split_store(hi_b, lo_b, off + 16, make_float4(r0.y, r1.y, r2.y, r3.y));
-          split_store(hi_b, lo_b, off + 32, make_float4(r0.z, r1.z, r2.z, r3.z));
-          split_store(hi_b, lo_b, off + 48, make_float4(r0.w, r1.w, r2.w, r3.w));
+        }
+    }
+  } else if (warp == 10) {
+    // ===================== activation-tile producer: lo block, then hi block of every job, in job order ============
+    if (lane == 0) {
+      uint32_t ph = 0;  // phase of the free barriers this job waits on (flips once per job)
+      for (int it = 0; it < my_tiles; ++it) {
+        const int64_t tile = blockIdx.x + (int64_t)it * gridDim.x;
+        for (int e = 0; e < E; ++e) {
+          const int nj = bp.n_jobs[e];
+          for (int i = 0; i < nj; ++i) {
+            const BwdJob& jq = bp.jobs[e][i];
+            const int w = jq.n_b;
+            const uint8_t* src = reinterpret_cast<const uint8_t*>(
+                                     stash + (size_t)P_pad * (jq.src_enc ? p.enc_cum[0] : p.g[jq.src].cum_n)) +
+                                 (size_t)tile * tile_bytes(w);
+            const uint32_t hb = (uint32_t)tile_half_bytes(w);
+            PROF_SCOPE(16, mbar_wait(xl_free, ph ^ 1));
+            mbar_arrive_expect_tx(xl_full, hb);
+            bulk_g2s(sX + 32768, src + hb, hb, xl_full);
+            PROF_SCOPE(17, mbar_wait(xh_free, ph ^ 1));
+            mbar_arrive_expect_tx(xh_full, hb);
+            bulk_g2s(sX, src, hb, xh_full);
+            ph ^= 1;
+          }
         }
       }
-      fence_proxy_async();
-      mbar_arrive(&op_full[os]);
     }
-  } else if (warp == kWarpMma) {
+  } else if (warp == 8) {
     // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
-    const uint32_t idesc = make_idesc(n_mma);
-    uint32_t os = 0, oph = 0;
-    for (int64_t s = 0; s < n_stage; ++s) {
-      mbar_wait(&op_full[os], oph);
-      tc_fence_after();
-      const uint32_t sb = smem_u32(sm + os * kStageBytesW);
-      if (elect_one()) {
-#pragma unroll
-        for (int j = 0; j < kStagePts / 8; ++j) {  // 8 points (two slabs) per instruction
-          const uint32_t a_hi = tmem + kColA + 64 * os + 8 * j;
-          const uint32_t a_lo = a_hi + 32;
-          const uint64_t b_hi = make_desc(sb + j * 2 * kSlabW, kSlabW, kSboW);
-          const uint64_t b_lo = make_desc(sb + kOpBytes + j * 2 * kSlabW, kSlabW, kSboW);
-          mma_ts(tmem + kColAccW, a_hi, b_hi, idesc, (s > 0 || j > 0) ? 1u : 0u);
-          mma_ts(tmem + kColAccW, a_lo, b_hi, idesc, 1u);
-          mma_ts(tmem + kColAccW, a_hi, b_lo, idesc, 1u);
+    Pipe pp;
+    uint32_t a_ph = 0, g_ph = 0, x_ph = 0, s0_ph = 0;
+    const uint32_t t_acc = tmem + kColAcc, t_ahi = tmem + kColAhi, t_alo = tmem + kColAlo;
+    const uint32_t gh = smem_u32(sG), gl = gh + 32768, xh = smem_u32(sX), xl = xh + 32768, ind = smem_u32(sInd);
+    for (int it = 0; it < my_tiles; ++it)
+      for (int e = 0; e < E; ++e) {
+        const GemmLayer& g = p.g[E - 1 - e];
+        if (e + 1 < E) {
+          // ---- chain: accumulator[p][k] = 2^11 sum_n G_t[p][n] W_t[n][k], N = k_h, K = n
+          const uint32_t idesc = make_idesc_f16(g.k_h);
+          const uint32_t slab_b = 16u * (uint32_t)g.k_h;
+          PROF_SCOPE(8, mbar_wait(bar_a, a_ph));
+          a_ph ^= 1;
+          tc_fence_after();
+          for (int ks = 0; ks < (g.n >> 4); ++ks) {
+            PROF_SCOPE(9, mbar_wait(&w_full[pp.stage], pp.phase));
+            tc_fence_after();
+            const uint32_t wb = smem_u32(sm + mp.ring + pp.stage * kWStage);
+            if (elect_one()) {
+              const uint64_t b_hs = make_desc(wb, slab_b, 128);
+              const uint64_t b_h = make_desc(wb + 2 * slab_b, slab_b, 128);
+              const uint64_t b_l = make_desc(wb + 4 * slab_b, slab_b, 128);
+              mma_ts_f16(t_acc, t_ahi + 8 * ks, b_hs, idesc, ks > 0 ? 1u : 0u);
+              mma_ts_f16(t_acc, t_alo + 8 * ks, b_h, idesc, 1u);
+              mma_ts_f16(t_acc, t_ahi + 8 * ks, b_l, idesc, 1u);
+              mma_commit(&w_empty[pp.stage]);
+            }
+            __syncwarp();
+            pp.advance(n_stages);
+          }
+          if (elect_one()) mma_commit(bar_acc);
+          __syncwarp();
+        } else {  // the last event of a tile (layer 0) has no chain MMA; keep bar_a's phase in step
+          mbar_wait(bar_a, a_ph);
+          a_ph ^= 1;
         }
-        mma_commit(&op_empty[os]);
+        // ---- weight-gradient jobs of this event
+        PROF_SCOPE(10, mbar_wait(bar_g, g_ph));
+        g_ph ^= 1;
+        tc_fence_after();
+        const int nj = bp.n_jobs[e];
+        for (int i = 0; i < nj; ++i) {
+          const BwdJob& jq = bp.jobs[e][i];
+          const int w = jq.n_b;
+          const uint32_t fstr = (uint32_t)(w >> 3) * 128u;  // bytes between 8-point blocks of the B tile
+          const uint32_t id_mn = make_idesc_f16_mn(w, 1, 1);
+          const uint32_t d = tmem + (uint32_t)jq.col;
+          if (jq.reuse_slot0) {
+            PROF_SCOPE(13, mbar_wait(slot0_free, s0_ph));
+            s0_ph ^= 1;
+            tc_fence_after();
+          }
+          // A = G^T: rows = features (SBO 128), K = points (LBO 16 * 128); one k-step = 16 points = 2 point blocks
+          PROF_SCOPE(11, mbar_wait(xl_full, x_ph));
+          tc_fence_after();
+          if (elect_one()) {
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks)
+              mma_ss_f16(d, make_desc(gh + ks * 4096, 2048, 128), make_desc(xl + ks * 2 * fstr, fstr, 128), id_mn,
+                         ks > 0 ? 1u : 0u);
+            mma_commit(xl_free);
+          }
+          __syncwarp();
+          PROF_SCOPE(12, mbar_wait(xh_full, x_ph));
+          tc_fence_after();
+          x_ph ^= 1;
+          if (elect_one()) {
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks)
+              mma_ss_f16(d, make_desc(gl + ks * 4096, 2048, 128), make_desc(xh + ks * 2 * fstr, fstr, 128), id_mn, 1u);
+            mma_ss_f16_scale11(d, make_desc(gh, 2048, 128), make_desc(xh, fstr, 128), id_mn);
+#pragma unroll
+            for (int ks = 1; ks < 8; ++ks)
+              mma_ss_f16(d, make_desc(gh + ks * 4096, 2048, 128), make_desc(xh + ks * 2 * fstr, fstr, 128), id_mn, 1u);
+            mma_commit(xh_free);
+            if (i == 0) {
+              // indicator job: sums[n][j] = sum over the points of ray j of the tile of G[p][n] (16 columns)
+              const uint32_t id16 = make_idesc_f16_mn(16, 1, 1);
+              const uint32_t di = tmem + kColInd;
+#pragma unroll
+              for (int ks = 0; ks < 8; ++ks)
+                mma_ss_f16(di, make_desc(gl + ks * 4096, 2048, 128), make_desc(ind + ks * 512, 256, 128), id16,
+                           ks > 0 ? 1u : 0u);
+              mma_ss_f16_scale11(di, make_desc(gh, 2048, 128), make_desc(ind, 256, 128), id16);
+#pragma unroll
+              for (int ks = 1; ks < 8; ++ks)
+                mma_ss_f16(di, make_desc(gh + ks * 4096, 2048, 128), make_desc(ind + ks * 512, 256, 128), id16, 1u);
+            }
+            mma_commit(&job_done[i]);
+          }
+          __syncwarp();
+        }
       }
-      __syncwarp();
-      if (++os == kOpStages) { os = 0; oph ^= 1; }
-    }
-    if (elect_one()) mma_commit(bar_done);
-    __syncwarp();
   } else {
-    // ===================== copy warp: one bulk copy per operand and stage, kRawStages deep =====================
-    uint32_t rs = 0, rph = 0;
-    for (int64_t s = 0; s < n_stage; ++s) {
-      const int64_t q0 = pt_begin + s * kStagePts;
-      const uint32_t rows = (uint32_t)min((int64_t)kStagePts, pt_end - q0);
-      mbar_wait(&raw_empty[rs], rph ^ 1);
-      if (elect_one()) {
-        uint8_t* dst = raw + rs * kRawBytes;
-        const uint32_t ba = rows * wa * 4, bb = rows * wb * 4;
-        mbar_arrive_expect_tx(&raw_full[rs], ba + bb);
-        bulk_g2s(dst, src_a + (size_t)q0 * wa, ba, &raw_full[rs]);
-        bulk_g2s(dst + kRawHalf, src_b + (size_t)q0 * wb, bb, &raw_full[rs]);
+    // ===================== epilogue warps =====================
+    const int row = tid & 127, half = tid >> 7;
+    const uint32_t lane_base = ((uint32_t)((warp & 3) * 32)) << 16;
+    const uint32_t t_acc = tmem + lane_base + kColAcc;
+    const uint32_t t_ahi = tmem + lane_base + kColAhi, t_alo = tmem + lane_base + kColAlo;
+    float* stg = reinterpret_cast<float*>(sm + mp.stg + half * 2 * kStgBytes);
+    uint32_t stg_n = 0;  // chunks this half has staged so far (selects the buffer)
+    uint32_t acc_ph = 0, job_ph[kMaxJobs] = {0u, 0u, 0u};
+    // previous event: what has to be drained before this event's G tile may be written
+    int prev_e = -1;
+    float prev_unscale = 0.f;
+    int prev_nrays = 0;
+
+    // drain the accumulators of event `de` (scale `us`): weight blocks -> gradient blob, indicator sums -> bias /
+    // direction-encoding accumulators in shared memory
+    auto drain_event = [&](const int de, const float us, const int n_rays_tile) {
+      const int nj = bp.n_jobs[de];
+      const int t = E - 1 - de;
+      const GemmLayer& g = p.g[t];
+      for (int i = 0; i < nj; ++i) {
+        PROF_SCOPE(3, mbar_wait(&job_done[i], job_ph[i]));
+        job_ph[i] ^= 1;
+        tc_fence_after();
+        const BwdJob& j = bp.jobs[de][i];
+        // 16-column chunks, alternating between the two halves; each half alternates between its two staging buffers
+        // and only waits for the bulk reduction issued two chunks ago before overwriting a buffer
+        const int nchunk = j.n_b >> 4;
+        for (int c = half; c < nchunk; c += 2) {
+          uint32_t v[16];
+          tmem_ld16(tmem + lane_base + (uint32_t)j.col + 16 * c, v);
+          float* sb = stg + (stg_n & 1u) * (kStgBytes / 4);
+          if (row == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // buffer (stg_n & 1) is free again
+          bar_half(half);
+          tmem_wait_ld();
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<float4*>(sb + row * 16 + ((q ^ ((row >> 1) & 3)) << 2)) =
+                make_float4(__uint_as_float(v[4 * q]) * us, __uint_as_float(v[4 * q + 1]) * us,
+                            __uint_as_float(v[4 * q + 2]) * us, __uint_as_float(v[4 * q + 3]) * us);
+          fence_proxy_async();
+          bar_half(half);
+          if (row == 0)
+            bulk_reduce_add_f32(gblob + j.gb_off + (size_t)c * 2048 + j.row0 * 16, sb + j.row0 * 16, (uint32_t)j.nrows * 64u);
+          ++stg_n;
+        }
+        if (i == 0) {
+          // indicator sums of this event: bias gradient (all rays) and, for layers_dir[0], the direction-encoding part
+          if (half == 0) {
+            uint32_t v16[16];
+            tmem_ld16(tmem + lane_base + kColInd, v16);
+            tmem_wait_ld();
+            float tot = 0.f;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) tot += __uint_as_float(v16[q]);
+            const float su = us * kActScale;  // the indicator is an exact 1, not an activation / 16
+            if (row < g.n) s_bgrad[g.cum_n + row] += tot * su;
+            if (de == 0 && p.use_viewdirs) {
+              if (row >= 64 && row < 68) s_bgrad[p.enc_cum[0] + row - 64] += tot * su;  // d_rgb, d_sigma sums
+              if (row < g.n)
+                for (int k = 0; k < p.dim_dir; ++k) {
+                  float a = 0.f;
+#pragma unroll
+                  for (int q = 0; q < kMaxRays; ++q)
+                    if (q < n_rays_tile) a = fmaf(__uint_as_float(v16[q]), s_encd[q * 32 + k], a);
+                  s_dgrad[row * 32 + k] += a * su;
+                }
+            }
+          }
+          if (nj == 3) {
+            tc_fence_before();
+            mbar_arrive(slot0_free);
+          }
+        }
       }
-      __syncwarp();
-      if (++rs == kRawStages) { rs = 0; rph ^= 1; }
+      tc_fence_before();
+    };
+
+    for (int it = 0; it < my_tiles; ++it) {
+      const int64_t tile = blockIdx.x + (int64_t)it * gridDim.x;
+      const int64_t p0 = tile * kTileRows;
+      int64_t pt = p0 + row;
+      const bool valid = pt < P;
+      if (!valid) pt = P - 1;
+      const int64_t first_ray = p0 / S;
+      const int64_t last_pt = (p0 + kTileRows - 1 < P) ? p0 + kTileRows - 1 : P - 1;
+      const int n_rays_tile = (int)(last_pt / S - first_ray) + 1;
+      const int ray_slot = (int)(pt / S - first_ray);
+      // ---- tile scale: max |d_raw| -> [4, 8)
+      const float4 d4 = valid ? reinterpret_cast<const float4*>(d_raw)[pt] : make_float4(0.f, 0.f, 0.f, 0.f);
+      {
+        const float m = fmaxf(fmaxf(fabsf(d4.x), fabsf(d4.y)), fmaxf(fabsf(d4.z), fabsf(d4.w)));
+        uint32_t mb = __float_as_uint(m);
+        mb = __reduce_max_sync(0xffffffffu, mb);
+        if (lane == 0) atomicMax(&s_max[it & 1], mb);
+        epi_bar256();
+        if (tid == 0) s_max[(it + 1) & 1] = 0u;  // reset the other slot for the next tile
+      }
+      const uint32_t ex = (s_max[it & 1] >> 23) & 0xFFu;
+      const bool scaled = ex >= 3u && ex <= 254u;
+      const float sc = scaled ? __uint_as_float((256u - ex) << 23) : 1.f;
+      const float unscale = (scaled ? __uint_as_float((ex - 2u) << 23) : 1.f) * kActInv;  // activations are stored / 16
+      const float dr[4] = {d4.x * sc, d4.y * sc, d4.z * sc, d4.w * sc};
+
+      for (int e = 0; e < E; ++e) {
+        const int t = E - 1 - e;
+        const GemmLayer& g = p.g[t];
+        const bool has_mma = e >= 1;
+        const bool has_next = e + 1 < E;
+        int hsel = -1;
+        if (p.h[0].src == t) hsel = 0;
+        if (p.n_head > 1 && p.h[1].src == t) hsel = 1;
+        const float* hw = hsel == 1 ? s_headw + hw1 : s_headw;
+        const int hk = hsel >= 0 ? p.h[hsel].k : 0, hn = hsel >= 0 ? p.h[hsel].n_out : 0;
+        const int hcol = hsel >= 0 ? p.h[hsel].out_col : 0;
+        // this row's ReLU mask words (fetched before the accumulator wait)
+        uint32_t mw[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};
+        if (g.relu) {
+          const uint32_t* mask_row = reinterpret_cast<const uint32_t*>(stash) + (size_t)P_pad * (p.mask_base + g.mask_cum) +
+                                     (size_t)pt * (g.n >> 5);
+          mw[0] = valid ? __ldg(mask_row + half) : 0u;
+          mw[1] = (valid && g.n == 128) ? __ldg(mask_row + 2 + half) : 0u;
+        }
+        if (has_mma) {
+          PROF_SCOPE(0, mbar_wait(bar_acc, acc_ph));
+          acc_ph ^= 1;
+          tc_fence_after();
+        }
+#ifdef NERFB200_PROF
+        const long long _ta = clock64();
+#endif
+        // ---------------- part A: G_t of this row -> hi / lo registers and tensor memory ----------------
+        // (both column chunks are pulled out of the accumulator before any arithmetic; the head term only exists for
+        // the two layers a head reads and stays out of the hot loop)
+        const int nch = g.n >> 6;
+        uint32_t hi[2][16], lo[2][16];
+        {
+          uint32_t v[2][32];
+          if (has_mma) {
+            tmem_ld32(t_acc + 32 * half, v[0]);
+            if (nch == 2) tmem_ld32(t_acc + 64 + 32 * half, v[1]);
+            tmem_wait_ld();
+          }
+#pragma unroll
+          for (int ch = 0; ch < 2; ++ch) {
+            if (ch < nch) {
+              const int c0 = 64 * ch + 32 * half;
+              float y[32];
+#pragma unroll
+              for (int q = 0; q < 32; ++q) y[q] = has_mma ? __uint_as_float(v[ch][q]) * kLoInv : 0.f;
+              if (hn > 0) {
+                for (int c = 0; c < hn; ++c) {
+                  const float dd = dr[(hcol + c) & 3];
+                  const float4* w4 = reinterpret_cast<const float4*>(hw + c * hk + c0);
+#pragma unroll
+                  for (int q = 0; q < 8; ++q) {
+                    const float4 w = w4[q];
+                    y[4 * q] = fmaf(dd, w.x, y[4 * q]);
+                    y[4 * q + 1] = fmaf(dd, w.y, y[4 * q + 1]);
+                    y[4 * q + 2] = fmaf(dd, w.z, y[4 * q + 2]);
+                    y[4 * q + 3] = fmaf(dd, w.w, y[4 * q + 3]);
+                  }
+                }
+              }
+              const uint32_t mword = mw[ch];
+#pragma unroll
+              for (int q = 0; q < 32; q += 2) {
+                const float y0 = (mword & (1u << q)) ? y[q] : 0.f;
+                const float y1 = (mword & (2u << q)) ? y[q + 1] : 0.f;
+                split_f16x2(y0, y1, hi[ch][q >> 1], lo[ch][q >> 1]);
+              }
+              if (has_next) {
+                tmem_st16(t_ahi + c0 / 2, hi[ch]);
+                tmem_st16(t_alo + c0 / 2, lo[ch]);
+              }
+            }
+          }
+        }
+        if (has_next) tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive(bar_a);
+
+        // ---------------- drain the previous event's jobs (they ran under part A) ----------------
+#ifdef NERFB200_PROF
+        const long long _tb = clock64();
+        if (tid == 0 && blockIdx.x == 0) g_prof[1] += (unsigned long long)(_tb - _ta);
+#endif
+        if (prev_e >= 0) drain_event(prev_e, prev_unscale, prev_nrays);
+#ifdef NERFB200_PROF
+        const long long _tc = clock64();
+        if (tid == 0 && blockIdx.x == 0) g_prof[2] += (unsigned long long)(_tc - _tb);
+#endif
+
+        // ---------------- part B: the held registers -> G tile (MN-major A operand of this event's jobs) ----------------
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+          if (ch < nch) {
+            const int fb0 = 8 * ch + 4 * half;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int off = tile_piece(row, fb0 + q, 128);
+              *reinterpret_cast<uint4*>(sG + off) = make_uint4(hi[ch][4 * q], hi[ch][4 * q + 1], hi[ch][4 * q + 2], hi[ch][4 * q + 3]);
+              *reinterpret_cast<uint4*>(sG + 32768 + off) =
+                  make_uint4(lo[ch][4 * q], lo[ch][4 * q + 1], lo[ch][4 * q + 2], lo[ch][4 * q + 3]);
+            }
+          }
+        }
+        if (nch == 1) {
+          // 64-wide layer (layers_dir[0], first event of a tile): feature rows 64..67 carry d_raw for the heads' weight
+          // gradients, the rest of the upper half is zero
+          const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+          if (half == 0) {
+            uint32_t h01, l01, h23, l23;
+            split_f16x2(dr[0], dr[1], h01, l01);
+            split_f16x2(dr[2], dr[3], h23, l23);
+            const int off = tile_piece(row, 8, 128);
+            *reinterpret_cast<uint4*>(sG + off) = make_uint4(h01, h23, 0u, 0u);
+            *reinterpret_cast<uint4*>(sG + 32768 + off) = make_uint4(l01, l23, 0u, 0u);
+#pragma unroll
+            for (int q = 9; q < 12; ++q) {
+              *reinterpret_cast<uint4*>(sG + tile_piece(row, q, 128)) = z4;
+              *reinterpret_cast<uint4*>(sG + 32768 + tile_piece(row, q, 128)) = z4;
+            }
+          } else {
+#pragma unroll
+            for (int q = 12; q < 16; ++q) {
+              *reinterpret_cast<uint4*>(sG + tile_piece(row, q, 128)) = z4;
+              *reinterpret_cast<uint4*>(sG + 32768 + tile_piece(row, q, 128)) = z4;
+            }
+          }
+        }
+        if (e == 0) {
+          // ray-indicator tile of this tile: I[p][j] = 1 iff point p belongs to the tile's j-th ray; direction encodings
+          if (half == 0) {
+            uint32_t w[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const uint32_t lo16 = (ray_slot == 2 * q && valid) ? 0x3C00u : 0u;
+              const uint32_t hi16 = (ray_slot == 2 * q + 1 && valid) ? 0x3C00u : 0u;
+              w[q] = lo16 | (hi16 << 16);
+            }
+            *reinterpret_cast<uint4*>(sInd + tile_piece(row, 0, 16)) = make_uint4(w[0], w[1], w[2], w[3]);
+            *reinterpret_cast<uint4*>(sInd + tile_piece(row, 1, 16)) = make_uint4(w[4], w[5], w[6], w[7]);
+          } else if (p.use_viewdirs && row < n_rays_tile * 3) {
+            const int jr = row / 3, c = row - 3 * jr;
+            const float vv = rays[(first_ray + jr) * ray_stride + 8 + c];
+            encode_coord(vv, c, p.inc_dir, 0, p.n_freq_dir, p.freq_dir, s_encd + jr * 32);
+          }
+        }
+        fence_proxy_async();
+        mbar_arrive(bar_g);
+#ifdef NERFB200_PROF
+        if (tid == 0 && blockIdx.x == 0) { g_prof[5] += (unsigned long long)(clock64() - _tc); g_prof[7] += 1; }
+#endif
+        prev_e = e;
+        prev_unscale = unscale;
+        prev_nrays = n_rays_tile;
+      }
+    }
+    if (prev_e >= 0) drain_event(prev_e, prev_unscale, prev_nrays);
+    if (row == 0) bulk_wait_all();
+    epi_bar256();
+    // ---- flush the bias / direction-encoding accumulators of this CTA
+    for (int gi = 0; gi < p.n_gemm; ++gi)
+      for (int i = tid; i < p.g[gi].n; i += kEpi) atomicAdd(flat_grad + p.g[gi].flat_b + i, s_bgrad[p.g[gi].cum_n + i]);
+    if (p.use_viewdirs) {
+      const GemmLayer& gd = p.g[p.n_gemm - 1];
+      const int in_real = gd.k_h + gd.enc_real;
+      for (int i = tid; i < gd.n * p.dim_dir; i += kEpi) {
+        const int n = i / p.dim_dir, k = i - n * p.dim_dir;
+        atomicAdd(flat_grad + gd.flat_w + (size_t)n * in_real + gd.k_h + k, s_dgrad[n * 32 + k]);
+      }
+      if (tid < 3) atomicAdd(flat_grad + p.h[1].flat_b + tid, s_bgrad[p.enc_cum[0] + tid]);
+      if (tid == 3) atomicAdd(flat_grad + p.h[0].flat_b, s_bgrad[p.enc_cum[0] + 3]);
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == kWarpMma) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemColsW));
+  if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemColsB));
 }
 
-int launch_wgrad_tc(const Plan& p, const float* rays, int ray_stride, const float* z, int64_t n_rays, int n_samples,
-                    const float* stash, const float* gstash, const float* d_raw, float* flat_grad, cudaStream_t s) {
-  (void)rays; (void)ray_stride; (void)z;  // the encodings come from the stash
-  if (p.hidden != 128) {
-    set_error("wgrad impl=1 (tcgen05): hidden_size %d not supported (128 only)", p.hidden);
+// gradient blob -> flat (torch-layout) gradient vector: every job block is [chunk][row][16 floats] with the four
+// 16-byte pieces of a row XOR-swizzled by ((row >> 1) & 3) (the staging tile's bank-conflict-free layout)
+__global__ void unpack_grad_kernel(const __grid_constant__ Plan p, const __grid_constant__ BwdPlan bp,
+                                   const float* __restrict__ gblob, float* __restrict__ flat_grad) {
+  const int gb_total = bp.gb_total;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < gb_total; idx += gridDim.x * blockDim.x) {
+    for (int e = 0; e < p.n_gemm; ++e) {
+      const int nj = bp.n_jobs[e];
+      bool done = false;
+      for (int i = 0; i < nj && !done; ++i) {
+        const BwdJob& j = bp.jobs[e][i];
+        const int sz = (j.n_b / 16) * 2048;
+        if (idx < j.gb_off || idx >= j.gb_off + sz) continue;
+        done = true;
+        const int r = idx - j.gb_off;
+        const int c = r >> 11, rr = (r >> 4) & 127, w = r & 15;
+        const int col = 16 * c + ((((w >> 2) ^ ((rr >> 1) & 3)) << 2) | (w & 3));
+        if (rr < j.row0 || rr >= j.row0 + j.nrows || col >= j.ncols) break;
+        const float v = gblob[idx];
+        if (j.dst_head >= 0) {
+          const HeadLayer& h = p.h[j.dst_head];
+          atomicAdd(flat_grad + h.flat_w + (size_t)(rr - j.row0) * h.k + col, v);
+        } else {
+          const GemmLayer& g = p.g[j.dst];
+          atomicAdd(flat_grad + g.flat_w + (size_t)rr * (g.k_h + g.enc_real) + j.dst_col0 + col, v);
+        }
+      }
+      if (done) break;
+    }
+  }
+}
+
+#ifdef NERFB200_PROF
+extern "C" void nerfb200_prof_read(unsigned long long* out32, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out32, g_prof, sizeof(g_prof));
+  if (reset) {
+    unsigned long long z[32] = {0};
+    cudaMemcpyToSymbol(g_prof, z, sizeof(z));
+  }
+}
+#endif
+
+
+int64_t bwd_tc_scratch_floats(const Plan& p) {
+  int total = 0;
+  bwd_jobs(p, 0, nullptr, &total);
+  return total;
+}
+
+int bwd_tc_supported(const Plan& p, int n_samples, const char* what) {
+  int rc = tc_supported(p, n_samples, what);
+  if (rc) return rc;
+  if (!p.use_viewdirs) {
+    set_error("%s impl=1 (tcgen05): the fused backward needs a view-dependent model (fc_rgb / fc_alpha heads); use impl=0", what);
     return NERFB200_ERR_UNSUPPORTED;
   }
-  const int64_t P = n_rays * n_samples;
-  const int items = wg_item_count(p);
-  const size_t bytes = (size_t)kOpStages * kStageBytesW + (size_t)kRawStages * kRawBytes + 256 + 1024;
-  int rc = check_cuda(cudaFuncSetAttribute(mlp_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes),
-                      "wgrad_tc smem attribute");
+  if (smem_map_b(p).n_stages < 2) {
+    set_error("%s impl=1 (tcgen05): network too deep for the backward's shared-memory budget; use impl=0", what);
+    return NERFB200_ERR_UNSUPPORTED;
+  }
+  return NERFB200_OK;
+}
+
+int launch_mlp_bwd_tc(const Plan& p, const float* blob, const float* rays, int ray_stride, int64_t n_rays, int n_samples,
+                      const float* d_raw, const float* stash, float* gblob, float* flat_grad, cudaStream_t s) {
+  int rc = bwd_tc_supported(p, n_samples, "mlp_bwd");
   if (rc) return rc;
+  const int64_t P = n_rays * n_samples;
+  const int64_t tiles = (P + kTileRows - 1) / kTileRows;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  // two full waves of one-CTA-per-SM, every item the same number of CTAs: a stage costs about the same for every
-  // item (measured: shares proportional to bytes per point are 10-30 % slower), and equal shares line the items'
-  // point ranges up, so rows two items share (dY of a layer with a skip input, X of the layer a head reads) are
-  // served from L2 the second time.
-  if (items > kWgMaxItems) {
-    set_error("wgrad impl=1 (tcgen05): %d work items exceed the grid table (%d)", items, kWgMaxItems);
-    return NERFB200_ERR_UNSUPPORTED;
-  }
-  const int64_t stages = (P + kStagePts - 1) / kStagePts;
-  int share = (2 * sms) / items;
-  if (share > stages) share = (int)stages;
-  if (share < 1) share = 1;
-  WgGrid grid;
-  grid.n_items = items;
-  for (int i = 0; i <= items; ++i) grid.start[i] = (short)(i * share);
-  mlp_wgrad_tc_kernel<<<grid.start[items], kThreadsW, bytes, s>>>(p, stash, gstash, d_raw, P, flat_grad, grid);
+  const int grid = (int)(tiles < sms ? tiles : sms);
+  const BwdPlan bp = make_bwd_plan(p);
+  const int gb_total = bp.gb_total;
+  rc = check_cuda(cudaMemsetAsync(gblob, 0, (size_t)gb_total * 4, s), "mlp_bwd_tc blob memset");
+  if (rc) return rc;
+  const size_t bytes = (size_t)smem_map_b(p).total + 1024;
+  rc = check_cuda(cudaFuncSetAttribute(mlp_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes),
+                  "mlp_bwd_tc smem attribute");
+  if (rc) return rc;
+  mlp_bwd_tc_kernel<<<grid, kThreadsB, bytes, s>>>(p, blob, rays, ray_stride, d_raw, stash, P, n_samples, tiles, gblob,
+                                                    flat_grad, bp);
   count_launch();
-  return check_cuda(cudaGetLastError(), "wgrad_tc launch");
+  rc = check_cuda(cudaGetLastError(), "mlp_bwd_tc launch");
+  if (rc) return rc;
+  int blocks = (gb_total + 255) / 256;
+  if (blocks > 1184) blocks = 1184;
+  unpack_grad_kernel<<<blocks, 256, 0, s>>>(p, bp, gblob, flat_grad);
+  count_launch();
+  return check_cuda(cudaGetLastError(), "unpack_grad launch");
 }
 
 }  // namespace nerfb200

@@ -120,6 +120,7 @@ __device__ __forceinline__ void mma_ts_f16(uint32_t d, uint32_t a_tmem, uint64_t
 //     hs = w_hi * 2^11,   h = w_hi,   l = (w - w_hi) * 2^11          (all fp16; |w| < 32 or hs overflows to inf)
 // and one k-step issues  a_hi*hs + a_lo*h + a_hi*l  =  2^11 * (a*w)  into ONE fp32 accumulator.
 constexpr float kLoScale = 2048.f, kLoInv = 1.f / 2048.f;
+constexpr float kActScale = 0.0625f, kActInv = 16.f;  // forward A operands / stash tiles hold activation / 16
 __device__ __forceinline__ void split_f16x2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
   asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
   float h0, h1;
@@ -201,9 +202,52 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// round-to-nearest (ties away) fp32 -> tf32 on the integer pipe: cvt.rna.tf32.f32 issues at conversion rate
-__device__ __forceinline__ uint32_t tf32_hi(float x) { return (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u; }
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+// ---------------------------------------------------------------------------------------------------------------
+// Operand tiles.  A 128-point x (8 F)-feature block of fp16 values is kept as 16 x F core matrices of 128 bytes,
+//     T[pb = point / 8][fb = feature / 8][point % 8][feature % 8]            (pb-major, F * 128 bytes per pb)
+// and a value x as two such blocks, hi = fp16(x) then lo = fp16((x - hi) 2^11)  (split_f16x2), 16 F 128 bytes apart.
+// The SAME bytes serve tcgen05.mma as
+//   K-major  operand (rows = points,   K = features): SBO = F * 128 (next 8 points),  LBO = 128 (next 8 features)
+//   MN-major operand (rows = features, K = points)  : SBO = 128 (next 8 features),    LBO = F * 128 (next 8 points)
+// (checked on hardware by tools/mn_test.cu), so the training forward writes every layer's activation tile ONCE --
+// into HBM, straight from the registers that also feed the next layer's tensor-memory operand -- and the fused
+// backward (mlp_tc_bwd.cu) bulk-copies it back and uses it as the B operand of the weight-gradient MMAs unchanged.
+// ---------------------------------------------------------------------------------------------------------------
+__host__ __device__ inline int tile_half_bytes(int n_feat) { return 16 * (n_feat >> 3) * 128; }   // one of hi / lo
+__host__ __device__ inline int tile_bytes(int n_feat) { return 2 * tile_half_bytes(n_feat); }      // = 128 * n * 4
+// byte offset of the 16-byte piece (point row, features [8 fb, 8 fb + 8)) inside the hi (or lo) block
+__host__ __device__ inline int tile_piece(int row, int fb, int n_feat) {
+  return (row >> 3) * (n_feat >> 3) * 128 + fb * 128 + (row & 7) * 16;
+}
+// instruction descriptor for kind::f16 with selectable operand majors (bit 15: A is MN-major, bit 16: B is MN-major)
+__device__ __forceinline__ uint32_t make_idesc_f16_mn(int n, int a_mn, int b_mn) {
+  return (1u << 4) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+}
+// D = A * B + D * 2^-11 (scale-input-d): folds the 2^11-scaled residual products into the main sum without a
+// second accumulator: first all lo*hi + hi*lo products, then the first hi*hi product with this variant
+__device__ __forceinline__ void mma_ss_f16_scale11(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, 1, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p, 11;\n}\n" ::"r"(d),
+      "l"(a), "l"(b), "r"(idesc)
+      : "memory");
+}
+// shared -> global bulk reduction (TMA engine): global[i] += shared[i], fp32
+__device__ __forceinline__ void bulk_reduce_add_f32(float* gdst, const void* ssrc, uint32_t bytes) {
+  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(gdst),
+               "r"(smem_u32(ssrc)), "r"(bytes)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+
+struct Pipe {  // role-local ring state
+  uint32_t stage = 0, phase = 0;
+  __device__ __forceinline__ void advance(uint32_t n_stages) {
+    if (++stage == n_stages) { stage = 0; phase ^= 1; }
+  }
+};
+
+__device__ __forceinline__ void epi_bar256() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 }  // namespace tc
 }  // namespace nerfb200

@@ -15,7 +15,7 @@ from . import _lib
 from ._lib import Arch, RenderOpts
 
 IMPL_SIMT = 0  # fp32 CUDA cores
-IMPL_TC = 1    # tcgen05 tensor cores (fp16x2 / 3xTF32 three-term splits, fp32 accumulation)
+IMPL_TC = 1    # tcgen05 tensor cores (fp16x2 three-term splits, fp32 accumulation)
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -192,10 +192,17 @@ def mlp_fwd(arch: ArchSpec, blob, rays, z, impl=IMPL_SIMT, want_stash=False):
     return (raw, stash) if want_stash else raw
 
 
+def impl_supported(arch: ArchSpec, n_samples: int, impl: int) -> bool:
+    """Can `impl` run this architecture forward and backward (the library decides, not Python)?"""
+    return _lib.load().nerfb200_impl_supported(C.byref(arch.c_struct()), int(n_samples), int(impl)) == _lib.OK
+
+
 def mlp_bwd(arch: ArchSpec, blob, rays, z, d_raw, stash, impl=IMPL_SIMT):
+    """Returns (flat_grad, scratch): scratch is the gradient stash for impl 0, the gradient blob for impl 1."""
     lib = _lib.load()
     n, s = z.shape
-    gstash = torch.empty_like(stash)
+    gstash = torch.empty(lib.nerfb200_bwd_scratch_floats(C.byref(arch.c_struct()), n * s, impl), dtype=torch.float32,
+                         device=z.device)
     flat_grad = torch.zeros(arch.flat_param_count(), dtype=torch.float32, device=z.device)
     _lib.check(lib.nerfb200_mlp_bwd(C.byref(arch.c_struct()), _ptr(blob), _ptr(rays), rays.shape[1], _ptr(z), n, s,
                                     _ptr(d_raw), _ptr(stash), _ptr(gstash), _ptr(flat_grad), impl, _stream()),
@@ -224,9 +231,9 @@ def mlp_wgrad(arch: ArchSpec, rays, z, d_raw, stash, gstash, impl=IMPL_SIMT, fla
     return flat_grad
 
 
-def wgrad_bytes_per_point(arch: ArchSpec) -> int:
-    """HBM bytes the tcgen05 wgrad kernel reads per point (one dY row + one X row per work item)."""
-    return int(_lib.load().nerfb200_wgrad_bytes_per_point(C.byref(arch.c_struct())))
+def bwd_bytes_per_point(arch: ArchSpec) -> int:
+    """HBM bytes the tcgen05 backward reads per point (activation tiles of its weight-gradient jobs, masks, d_raw)."""
+    return int(_lib.load().nerfb200_bwd_bytes_per_point(C.byref(arch.c_struct())))
 
 
 def composite_fwd(raw, z, rays, noise, noise_std, white_bkgd, want_weights=True):

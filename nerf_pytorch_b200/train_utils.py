@@ -32,8 +32,8 @@ DEFAULT_IMPL = None
 
 
 def _auto_impl(arch_c, arch_f, n_coarse, n_fine):
-    ok = all(a is None or (a.hidden == 128 and a.dim_xyz <= 64 and a.dim_dir <= 32) for a in (arch_c, arch_f))
-    return ops.IMPL_TC if ok and n_coarse >= 16 else ops.IMPL_SIMT
+    ok = all(a is None or ops.impl_supported(a, n_coarse, ops.IMPL_TC) for a in (arch_c, arch_f))
+    return ops.IMPL_TC if ok else ops.IMPL_SIMT
 
 # gradient synchronisation across ranks: (process_group, world_size) or None; see parallel.py
 _GRAD_SYNC = None

@@ -8,7 +8,7 @@ impl = int(os.environ.get("IMPL", "0")); archname = os.environ.get("ARCH", "A1")
 kw = {"A0": dict(num_layers=4, hidden=128, skip_every=4), "A1": dict(num_layers=8, hidden=128, skip_every=3),
       "A2": dict(num_layers=8, hidden=256, skip_every=4)}[archname]
 arch = ops.ArchSpec(n_freq_xyz=10, n_freq_dir=4, **kw)
-N, S = 4096, 192
+N, S = int(os.environ.get("NRAYS", "4096")), 192
 torch.manual_seed(0)
 flat = torch.randn(arch.flat_param_count(), device="cuda") * 0.05
 blob = ops.pack_weights(arch, flat)

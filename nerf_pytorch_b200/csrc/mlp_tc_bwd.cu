@@ -23,12 +23,13 @@
 //              (tcgen05.ld -> unscale -> swizzled staging tile -> cp.reduce.async.bulk .add.f32 into the L2-resident
 //              gradient blob);  part B: the held hi / lo registers -> shared-memory G tile.
 //   warp 8     MMA issuer: chain MMA of the layer (A from tensor memory, B = weights from the ring), then the layer's
-//              weight-gradient jobs (A = G tile, B = activation tile, both MN-major from shared memory) and the
-//              16-column ray-indicator job that yields the bias gradients and the per-ray sums of layers_dir[0].
+//              weight-gradient jobs (A = G tile, B = activation tile, both MN-major from shared memory), the
+//              16-column ray-indicator job that yields the bias gradients and the per-ray sums of layers_dir[0], and
+//              the two narrow heads' jobs with the roles swapped (A = activation tile, B = a 16-column d_raw tile).
 //   warp 9     weight producer (cp.async.bulk ring, one k-step per stage)
 //   warp 10    activation-tile producer (hi block / lo block of one job at a time)
 // Tensor memory: [0,128) chain accumulator, [128,256) chain A operand (hi | lo), [256,384) job slot 0,
-// [384,400) indicator sums, [400,464) job slot 1 (jobs at most 64 wide).
+// [384,400) indicator sums, [400,464) job slot 1 (jobs at most 64 wide), [464,480) / [480,496) the heads' jobs.
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -45,11 +46,12 @@ constexpr int kStgBytes = 8192;                   // staging chunk: 128 rows x 1
 constexpr int kIndBytes = 4096;                   // ray-indicator tile: 128 points x 16 "features" (hi only)
 constexpr int kMaxRays = 10;
 constexpr uint32_t kTmemColsB = 512;
-constexpr uint32_t kColAcc = 0, kColAhi = 128, kColAlo = 192, kColSlot0 = 256, kColInd = 384, kColSlot1 = 400;
+constexpr uint32_t kColAcc = 0, kColAhi = 128, kColAlo = 192, kColSlot0 = 256, kColInd = 384, kColSlot1 = 400,
+                   kColHead0 = 464;  // + 16 per head job
 constexpr int kSmemLimitB = 232448 - 1024;
 
 struct SmemMapB {
-  int g, x, stg, ind, headw, bgrad, dgrad, encd, misc, bars, ring, total, n_stages;
+  int g, x, stg, ind, dtile, headw, bgrad, dgrad, encd, misc, bars, ring, total, n_stages;
 };
 __host__ __device__ inline SmemMapB smem_map_b(const Plan& p) {
   SmemMapB m;
@@ -58,9 +60,10 @@ __host__ __device__ inline SmemMapB smem_map_b(const Plan& p) {
   m.x = off;      off += kXBytes;
   m.stg = off;    off += 4 * kStgBytes;
   m.ind = off;    off += kIndBytes;
+  m.dtile = off;  off += 2 * kIndBytes;           // d_raw as a 16-column operand tile (hi block, lo block)
   m.headw = off;  off += (4 * 128 + 3 * 64 + 16) * 4;
   m.bgrad = off;  off += (p.enc_cum[0] + 8) * 4;   // bias gradients of every gemm layer + the heads' (8)
-  m.dgrad = off;  off += 64 * 32 * 4;              // direction-encoding part of dW(layers_dir[0]): [n][e]
+  m.dgrad = off;  off += 64 * 28 * 4;              // direction-encoding part of dW(layers_dir[0]): [n][e], e < 28
   m.encd = off;   off += kMaxRays * 32 * 4;
   m.misc = off;   off += 64;
   m.bars = off;   off += 256;
@@ -85,7 +88,7 @@ struct BwdJob {
   int dst;       // gemm index
   int dst_col0;  // first input column of the destination weight this block covers
   int ncols;     // real columns
-  int reuse_slot0;  // must wait until the first job of the event has been drained
+  int kind;      // 0: A = G tile, B = activation tile;  1: head job, A = activation tile (rows = its features), B = d_raw tile
 };
 constexpr int kMaxJobs = 3;
 
@@ -98,19 +101,19 @@ __host__ __device__ inline int bwd_jobs(const Plan& p, int e, BwdJob* out, int* 
     int n = 0;
     BwdJob jb[kMaxJobs];
     auto add = [&](int src_enc, int src, int n_b, int col, int row0, int nrows, int dst_head, int dst, int dst_col0,
-                   int ncols, int reuse) {
+                   int ncols, int kind) {
       BwdJob& j = jb[n++];
       j.src_enc = src_enc; j.src = src; j.n_b = n_b; j.col = col; j.row0 = row0; j.nrows = nrows;
-      j.gb_off = gb; j.dst_head = dst_head; j.dst = dst; j.dst_col0 = dst_col0; j.ncols = ncols; j.reuse_slot0 = reuse;
-      gb += (n_b / 16) * 128 * 16;
+      j.gb_off = gb; j.dst_head = dst_head; j.dst = dst; j.dst_col0 = dst_col0; j.ncols = ncols; j.kind = kind;
+      if (kind == 0) gb += (n_b / 16) * 128 * 16;
     };
     if (g.k_h > 0) add(0, g.src, g.k_h, (int)kColSlot0, 0, g.n, -1, t, 0, g.k_h, 0);
     if (g.k_enc > 0 && g.enc_sel == 0)
       add(1, 0, p.enc_tile_w, g.k_h > 0 ? (int)kColSlot1 : (int)kColSlot0, 0, g.n, -1, t, g.k_h, g.enc_real, 0);
     if (p.use_viewdirs && t == p.n_gemm - 1) {
-      // the heads ride on the spare rows of the 64-wide layers_dir[0] tile: rows 64..66 = d_rgb, row 67 = d_sigma
-      add(0, t, g.n, (int)kColSlot1, 64, 3, 1, t, 0, p.h[1].k, 0);                            // fc_rgb reads this layer's output
-      add(0, p.h[0].src, p.g[p.h[0].src].n, (int)kColSlot0, 67, 1, 0, t, 0, p.h[0].k, 1);     // fc_alpha reads the trunk output
+      // the narrow heads: dW_head[c][k] = sum_p d_raw[p][c] X[p][k] with the activation tile on the M side
+      add(0, t, g.n, (int)kColHead0, 0, p.h[1].k, 1, t, 0, 16, 1);                               // fc_rgb reads this layer's output
+      add(0, p.h[0].src, p.g[p.h[0].src].n, (int)kColHead0 + 16, 0, p.h[0].k, 0, t, 0, 16, 1);   // fc_alpha reads the trunk output
     }
     if (ev == e && out)
       for (int i = 0; i < n; ++i) out[i] = jb[i];
@@ -163,6 +166,7 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
   uint8_t* sG = sm + mp.g;
   uint8_t* sX = sm + mp.x;
   uint8_t* sInd = sm + mp.ind;
+  uint8_t* sD = sm + mp.dtile;
   float* s_headw = reinterpret_cast<float*>(sm + mp.headw);
   float* s_bgrad = reinterpret_cast<float*>(sm + mp.bgrad);
   float* s_dgrad = reinterpret_cast<float*>(sm + mp.dgrad);
@@ -179,8 +183,7 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
   uint64_t* xh_free = xl_full + 1;
   uint64_t* xl_free = xh_free + 1;
   uint64_t* job_done = xl_free + 1;             // [kMaxJobs]: job i of the running event complete
-  uint64_t* slot0_free = job_done + kMaxJobs;   // first job of a three-job event drained
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(slot0_free + 1);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(job_done + kMaxJobs);
   const uint32_t n_stages = (uint32_t)mp.n_stages;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -202,7 +205,6 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
     mbar_init(xh_free, 1);
     mbar_init(xl_free, 1);
     for (int i = 0; i < kMaxJobs; ++i) mbar_init(&job_done[i], 1);
-    mbar_init(slot0_free, kEpi);
     fence_barrier_init();
     s_max[0] = s_max[1] = 0u;
   }
@@ -214,9 +216,10 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
   for (int i = tid; i < hw1; i += kThreadsB) s_headw[i] = blob[p.h[0].w_off + i];
   for (int i = tid; i < hw2; i += kThreadsB) s_headw[hw1 + i] = blob[p.h[1].w_off + i];
   for (int i = tid; i < p.enc_cum[0] + 8; i += kThreadsB) s_bgrad[i] = 0.f;
-  for (int i = tid; i < 64 * 32; i += kThreadsB) s_dgrad[i] = 0.f;
+  for (int i = tid; i < 64 * 28; i += kThreadsB) s_dgrad[i] = 0.f;
   for (int i = tid; i < kMaxRays * 32; i += kThreadsB) s_encd[i] = 0.f;
   for (int i = tid; i < kGBytes / 16; i += kThreadsB) reinterpret_cast<uint4*>(sG)[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = tid; i < 2 * kIndBytes / 16; i += kThreadsB) reinterpret_cast<uint4*>(sD)[i] = make_uint4(0u, 0u, 0u, 0u);
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
@@ -272,9 +275,10 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
   } else if (warp == 8) {
     // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
     Pipe pp;
-    uint32_t a_ph = 0, g_ph = 0, x_ph = 0, s0_ph = 0;
+    uint32_t a_ph = 0, g_ph = 0, x_ph = 0;
     const uint32_t t_acc = tmem + kColAcc, t_ahi = tmem + kColAhi, t_alo = tmem + kColAlo;
     const uint32_t gh = smem_u32(sG), gl = gh + 32768, xh = smem_u32(sX), xl = xh + 32768, ind = smem_u32(sInd);
+    const uint32_t dh = smem_u32(sD), dl = dh + kIndBytes;
     for (int it = 0; it < my_tiles; ++it)
       for (int e = 0; e < E; ++e) {
         const GemmLayer& g = p.g[E - 1 - e];
@@ -315,14 +319,38 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
         for (int i = 0; i < nj; ++i) {
           const BwdJob& jq = bp.jobs[e][i];
           const int w = jq.n_b;
-          const uint32_t fstr = (uint32_t)(w >> 3) * 128u;  // bytes between 8-point blocks of the B tile
-          const uint32_t id_mn = make_idesc_f16_mn(w, 1, 1);
+          const uint32_t fstr = (uint32_t)(w >> 3) * 128u;  // bytes between 8-point blocks of the activation tile
           const uint32_t d = tmem + (uint32_t)jq.col;
-          if (jq.reuse_slot0) {
-            PROF_SCOPE(13, mbar_wait(slot0_free, s0_ph));
-            s0_ph ^= 1;
+          if (jq.kind == 1) {
+            // head job: A = activation tile (rows = its features: SBO 128, K = points: LBO fstr), B = d_raw tile (N = 16)
+            const uint32_t id16 = make_idesc_f16_mn(16, 1, 1);
+            PROF_SCOPE(11, mbar_wait(xl_full, x_ph));
             tc_fence_after();
+            if (elect_one()) {
+#pragma unroll
+              for (int ks = 0; ks < 8; ++ks)
+                mma_ss_f16(d, make_desc(xl + ks * 2 * fstr, fstr, 128), make_desc(dh + ks * 512, 256, 128), id16, ks > 0 ? 1u : 0u);
+              mma_commit(xl_free);
+            }
+            __syncwarp();
+            PROF_SCOPE(12, mbar_wait(xh_full, x_ph));
+            tc_fence_after();
+            x_ph ^= 1;
+            if (elect_one()) {
+#pragma unroll
+              for (int ks = 0; ks < 8; ++ks)
+                mma_ss_f16(d, make_desc(xh + ks * 2 * fstr, fstr, 128), make_desc(dl + ks * 512, 256, 128), id16, 1u);
+              mma_ss_f16_scale11(d, make_desc(xh, fstr, 128), make_desc(dh, 256, 128), id16);
+#pragma unroll
+              for (int ks = 1; ks < 8; ++ks)
+                mma_ss_f16(d, make_desc(xh + ks * 2 * fstr, fstr, 128), make_desc(dh + ks * 512, 256, 128), id16, 1u);
+              mma_commit(xh_free);
+              mma_commit(&job_done[i]);
+            }
+            __syncwarp();
+            continue;
           }
+          const uint32_t id_mn = make_idesc_f16_mn(w, 1, 1);
           // A = G^T: rows = features (SBO 128), K = points (LBO 16 * 128); one k-step = 16 points = 2 point blocks
           PROF_SCOPE(11, mbar_wait(xl_full, x_ph));
           tc_fence_after();
@@ -389,6 +417,19 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
         job_ph[i] ^= 1;
         tc_fence_after();
         const BwdJob& j = bp.jobs[de][i];
+        if (j.kind == 1) {
+          // head job: lane = input feature k of the head, columns = d_raw channels: dW_head[c][k], a handful of atomics
+          if (half == 0) {
+            uint32_t v16[16];
+            tmem_ld16(tmem + lane_base + (uint32_t)j.col, v16);
+            tmem_wait_ld();
+            const HeadLayer& h = p.h[j.dst_head];
+            if (row < h.k)
+              for (int c = 0; c < h.n_out; ++c)
+                atomicAdd(flat_grad + h.flat_w + (size_t)c * h.k + row, __uint_as_float(v16[(h.out_col + c) & 15]) * us);
+          }
+          continue;
+        }
         // 16-column chunks, alternating between the two halves; each half alternates between its two staging buffers
         // and only waits for the bulk reduction issued two chunks ago before overwriting a buffer
         const int nchunk = j.n_b >> 4;
@@ -429,13 +470,9 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
 #pragma unroll
                   for (int q = 0; q < kMaxRays; ++q)
                     if (q < n_rays_tile) a = fmaf(__uint_as_float(v16[q]), s_encd[q * 32 + k], a);
-                  s_dgrad[row * 32 + k] += a * su;
+                  s_dgrad[row * 28 + k] += a * su;
                 }
             }
-          }
-          if (nj == 3) {
-            tc_fence_before();
-            mbar_arrive(slot0_free);
           }
         }
       }
@@ -607,10 +644,18 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
             }
             *reinterpret_cast<uint4*>(sInd + tile_piece(row, 0, 16)) = make_uint4(w[0], w[1], w[2], w[3]);
             *reinterpret_cast<uint4*>(sInd + tile_piece(row, 1, 16)) = make_uint4(w[4], w[5], w[6], w[7]);
-          } else if (p.use_viewdirs && row < n_rays_tile * 3) {
-            const int jr = row / 3, c = row - 3 * jr;
-            const float vv = rays[(first_ray + jr) * ray_stride + 8 + c];
-            encode_coord(vv, c, p.inc_dir, 0, p.n_freq_dir, p.freq_dir, s_encd + jr * 32);
+          } else {
+            // d_raw of this point as a 16-column operand tile (columns 0..3 live): B operand of the heads' jobs
+            uint32_t h01, l01, h23, l23;
+            split_f16x2(dr[0], dr[1], h01, l01);
+            split_f16x2(dr[2], dr[3], h23, l23);
+            *reinterpret_cast<uint4*>(sD + tile_piece(row, 0, 16)) = make_uint4(h01, h23, 0u, 0u);
+            *reinterpret_cast<uint4*>(sD + kIndBytes + tile_piece(row, 0, 16)) = make_uint4(l01, l23, 0u, 0u);
+            if (p.use_viewdirs && row < n_rays_tile * 3) {
+              const int jr = row / 3, c = row - 3 * jr;
+              const float vv = rays[(first_ray + jr) * ray_stride + 8 + c];
+              encode_coord(vv, c, p.inc_dir, 0, p.n_freq_dir, p.freq_dir, s_encd + jr * 32);
+            }
           }
         }
         fence_proxy_async();
@@ -634,7 +679,7 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
       const int in_real = gd.k_h + gd.enc_real;
       for (int i = tid; i < gd.n * p.dim_dir; i += kEpi) {
         const int n = i / p.dim_dir, k = i - n * p.dim_dir;
-        atomicAdd(flat_grad + gd.flat_w + (size_t)n * in_real + gd.k_h + k, s_dgrad[n * 32 + k]);
+        atomicAdd(flat_grad + gd.flat_w + (size_t)n * in_real + gd.k_h + k, s_dgrad[n * 28 + k]);
       }
       if (tid < 3) atomicAdd(flat_grad + p.h[1].flat_b + tid, s_bgrad[p.enc_cum[0] + tid]);
       if (tid == 3) atomicAdd(flat_grad + p.h[0].flat_b, s_bgrad[p.enc_cum[0] + 3]);
@@ -657,6 +702,7 @@ __global__ void unpack_grad_kernel(const __grid_constant__ Plan p, const __grid_
       bool done = false;
       for (int i = 0; i < nj && !done; ++i) {
         const BwdJob& j = bp.jobs[e][i];
+        if (j.kind != 0) continue;
         const int sz = (j.n_b / 16) * 2048;
         if (idx < j.gb_off || idx >= j.gb_off + sz) continue;
         done = true;
@@ -665,13 +711,8 @@ __global__ void unpack_grad_kernel(const __grid_constant__ Plan p, const __grid_
         const int col = 16 * c + ((((w >> 2) ^ ((rr >> 1) & 3)) << 2) | (w & 3));
         if (rr < j.row0 || rr >= j.row0 + j.nrows || col >= j.ncols) break;
         const float v = gblob[idx];
-        if (j.dst_head >= 0) {
-          const HeadLayer& h = p.h[j.dst_head];
-          atomicAdd(flat_grad + h.flat_w + (size_t)(rr - j.row0) * h.k + col, v);
-        } else {
-          const GemmLayer& g = p.g[j.dst];
-          atomicAdd(flat_grad + g.flat_w + (size_t)rr * (g.k_h + g.enc_real) + j.dst_col0 + col, v);
-        }
+        const GemmLayer& g = p.g[j.dst];
+        atomicAdd(flat_grad + g.flat_w + (size_t)rr * (g.k_h + g.enc_real) + j.dst_col0 + col, v);
       }
       if (done) break;
     }

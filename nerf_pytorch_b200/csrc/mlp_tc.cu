@@ -298,7 +298,10 @@ mlp_fwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
         const uint32_t slab_b = 16u * (uint32_t)mi.n_mma;  // bytes of one weight slab
         const uint32_t t_acc = tmem + s * kSlotCols + kColAcc;
         const uint32_t t_ahi = tmem + s * kSlotCols + kColAhi, t_alo = tmem + s * kSlotCols + kColAlo;
-        const uint32_t e_hi = smem_u32(sm + mp.enc + s * kEncBytes);
+        // descriptors are built once per layer; the loops below only advance their start-address fields
+        const uint64_t b_ring = make_desc(smem_u32(sm + mp.ring), slab_b, 128);
+        const uint64_t e_hi_d0 = make_desc(smem_u32(sm + mp.enc + s * kEncBytes), 128, (uint32_t)(enc_w >> 3) * 128u);
+        const uint64_t e_lo_d0 = desc_adv(e_hi_d0, (uint32_t)enc_half);
         constexpr int kHalfSteps = 4;  // k-steps covered by A columns [0, 64)
         mbar_wait(&bar_a1[s], a_phase[s]);
         tc_fence_after();
@@ -311,16 +314,15 @@ mlp_fwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
           }
           mbar_wait(&bar_full[pp.stage], pp.phase);
           tc_fence_after();
-          const uint32_t wb0 = smem_u32(sm + mp.ring + pp.stage * kStageBytes);
+          const uint64_t b_st = desc_adv(b_ring, pp.stage * (uint32_t)kStageBytes);
           if (elect_one()) {
 #pragma unroll
             for (int h = 0; h < kStepsPerStage; ++h) {
               const int ks = ks0 + h;
               if (ks < mi.ksteps) {
-                const uint32_t wb = wb0 + h * 6 * slab_b;
-                const uint64_t b_hs = make_desc(wb, slab_b, 128);
-                const uint64_t b_h = make_desc(wb + 2 * slab_b, slab_b, 128);
-                const uint64_t b_l = make_desc(wb + 4 * slab_b, slab_b, 128);
+                const uint64_t b_hs = desc_adv(b_st, h * 6 * slab_b);
+                const uint64_t b_h = desc_adv(b_hs, 2 * slab_b);
+                const uint64_t b_l = desc_adv(b_hs, 4 * slab_b);
                 const uint32_t acc0 = ks > 0 ? 1u : 0u;
                 if (ks < mi.ksteps_h) {
                   mma_ts_f16(t_acc, t_ahi + 8 * ks, b_hs, idesc, acc0);
@@ -328,8 +330,7 @@ mlp_fwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
                   mma_ts_f16(t_acc, t_ahi + 8 * ks, b_l, idesc, 1u);
                 } else {  // encodings: K-major view of the operand tile (SBO = next 8 points, LBO = next 8 features)
                   const uint32_t off = (uint32_t)(ks - mi.ksteps_h) * 256u;
-                  const uint64_t e_hi_d = make_desc(e_hi + off, 128, (uint32_t)(enc_w >> 3) * 128u);
-                  const uint64_t e_lo_d = make_desc(e_hi + enc_half + off, 128, (uint32_t)(enc_w >> 3) * 128u);
+                  const uint64_t e_hi_d = desc_adv(e_hi_d0, off), e_lo_d = desc_adv(e_lo_d0, off);
                   mma_ss_f16(t_acc, e_hi_d, b_hs, idesc, acc0);
                   mma_ss_f16(t_acc, e_lo_d, b_h, idesc, 1u);
                   mma_ss_f16(t_acc, e_hi_d, b_l, idesc, 1u);

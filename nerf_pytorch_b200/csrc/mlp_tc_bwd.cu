@@ -6,8 +6,8 @@
 //   wgrad  : dW_t[n][k] += sum_p G_t[p][n] X_{t-1}[p][k]                                    (M = features n, K = points)
 // Both are 3-term split-precision products on tcgen05.mma.kind::f16 (tc_common.cuh split_f16x2).  The trick that
 // makes the fusion cheap is the operand tile (tc_common.cuh "Operand tiles"): G_t is split into fp16 hi / lo ONCE in
-// the epilogue registers; the same registers go to tensor memory (A operand of the chain, K-major) and to a
-// shared-memory tile whose MN-major view is the A operand of the weight-gradient MMAs; the forward stashed every
+// the epilogue registers and stored ONCE to a shared-memory tile: its K-major view is the A operand of the chain MMA,
+// its MN-major view the A operand of the weight-gradient MMAs; the forward stashed every
 // layer's activation X_t as the same kind of tile, so the B operand of the weight-gradient MMAs is a plain bulk copy
 // from HBM.  Nothing is transposed on the CUDA cores.
 //
@@ -17,26 +17,31 @@
 // both sides); they are accumulated first and folded in by the scale-input-d form of the first hi*hi MMA
 // (D = A*B + D * 2^-11), so a weight gradient needs ONE accumulator and no pre-scaled operand copies.
 //
-// Persistent kernel, one CTA per SM, 352 threads:
-//   warps 0-7  epilogue (thread = (point row, column half)): per layer  part A: accumulator -> + head term, ReLU mask,
-//              split -> tensor memory (chain A operand);  drain the previous layer's weight-gradient accumulators
-//              (tcgen05.ld -> unscale -> swizzled staging tile -> cp.reduce.async.bulk .add.f32 into the L2-resident
-//              gradient blob);  part B: the held hi / lo registers -> shared-memory G tile.
-//   warp 8     MMA issuer: chain MMA of the layer (A from tensor memory, B = weights from the ring), then the layer's
+// Persistent kernel, one CTA per SM, 512 threads (register file rebalanced between the roles with setmaxnreg):
+//   warps 0-7  epilogue (thread = (point row, column half)): per layer  part A: chain accumulator -> + head term, ReLU
+//              mask, split into hi / lo registers;  part B (once the previous layer's jobs have finished reading the
+//              G tile): registers -> shared-memory G tile.
+//   warp 8     MMA issuer: chain MMA of the layer (A = G tile, K-major view; B = weights from the ring), then the layer's
 //              weight-gradient jobs (A = G tile, B = activation tile, both MN-major from shared memory), the
 //              16-column ray-indicator job that yields the bias gradients and the per-ray sums of layers_dir[0], and
 //              the two narrow heads' jobs with the roles swapped (A = activation tile, B = a 16-column d_raw tile).
 //   warp 9     weight producer (cp.async.bulk ring, one k-step per stage)
 //   warp 10    activation-tile producer (hi block / lo block of one job at a time)
-// Tensor memory: [0,128) chain accumulator, [128,256) chain A operand (hi | lo), [256,384) job slot 0,
-// [384,400) indicator sums, [400,464) job slot 1 (jobs at most 64 wide), [464,480) / [480,496) the heads' jobs.
+//   warps 12-15 drain (thread = accumulator row): the finished weight-gradient accumulators, up to two layers behind
+//              the issuer (they are double-buffered in tensor memory by layer parity): tcgen05.ld -> unscale ->
+//              swizzled staging chunk (4 x 8 KB, rotating) -> cp.reduce.async.bulk .add.f32 into the L2-resident
+//              gradient blob; indicator sums -> bias / direction-encoding accumulators; heads' rows -> atomics.
+// Tensor memory: [0,128) chain accumulator; two buffers of 144 columns at 128 and 272 (main job 128 + indicator sums
+// 16), used alternately by consecutive layers; [416,480) the second job of a layer (encoding part of a skip layer /
+// of layer1's neighbour, at most 64 wide); [480,496) / [496,512) the heads' jobs.
 #include "common.cuh"
 #include "tc_common.cuh"
 
 namespace nerfb200 {
 
 namespace tcb {
-constexpr int kThreadsB = 352;
+constexpr int kThreadsB = 512;
+constexpr int kDrainWarp0 = 12, kDrainThreads = 128;
 constexpr int kEpi = 256;
 constexpr int kWStage = 96 * 128;                 // one k-step of a 128-wide layer: 3 copies x 2 slabs x 128 x 16 B
 constexpr int kMaxWStages = 6;
@@ -46,8 +51,7 @@ constexpr int kStgBytes = 8192;                   // staging chunk: 128 rows x 1
 constexpr int kIndBytes = 4096;                   // ray-indicator tile: 128 points x 16 "features" (hi only)
 constexpr int kMaxRays = 10;
 constexpr uint32_t kTmemColsB = 512;
-constexpr uint32_t kColAcc = 0, kColAhi = 128, kColAlo = 192, kColSlot0 = 256, kColInd = 384, kColSlot1 = 400,
-                   kColHead0 = 464;  // + 16 per head job
+constexpr uint32_t kColAcc = 0, kColMain = 128, kMainStride = 144, kIndOff = 128, kColSecond = 416, kColHead0 = 480;
 constexpr int kSmemLimitB = 232448 - 1024;
 
 struct SmemMapB {
@@ -81,7 +85,8 @@ struct BwdJob {
   int src_enc;   // B tile: 1 = the xyz-encoding tile, 0 = the stashed output of gemm layer `src`
   int src;
   int n_b;       // columns = width of the B tile (multiple of 16)
-  int col;       // tensor-memory column of the accumulator
+  int col;       // tensor-memory column of the accumulator (main jobs: of buffer 0; + kMainStride for odd layers)
+  int dbuf;      // 1: double-buffered by layer parity
   int row0, nrows;  // accumulator rows that carry gradients
   int gb_off;    // float offset of this job's block in the gradient blob: [n_b / 16 chunks][128 rows][16]
   int dst_head;  // -1: rows are output features of gemm layer `dst`; else head index, rows row0.. are its outputs
@@ -105,11 +110,12 @@ __host__ __device__ inline int bwd_jobs(const Plan& p, int e, BwdJob* out, int* 
       BwdJob& j = jb[n++];
       j.src_enc = src_enc; j.src = src; j.n_b = n_b; j.col = col; j.row0 = row0; j.nrows = nrows;
       j.gb_off = gb; j.dst_head = dst_head; j.dst = dst; j.dst_col0 = dst_col0; j.ncols = ncols; j.kind = kind;
+      j.dbuf = (col == (int)kColMain) ? 1 : 0;
       if (kind == 0) gb += (n_b / 16) * 128 * 16;
     };
-    if (g.k_h > 0) add(0, g.src, g.k_h, (int)kColSlot0, 0, g.n, -1, t, 0, g.k_h, 0);
+    if (g.k_h > 0) add(0, g.src, g.k_h, (int)kColMain, 0, g.n, -1, t, 0, g.k_h, 0);
     if (g.k_enc > 0 && g.enc_sel == 0)
-      add(1, 0, p.enc_tile_w, g.k_h > 0 ? (int)kColSlot1 : (int)kColSlot0, 0, g.n, -1, t, g.k_h, g.enc_real, 0);
+      add(1, 0, p.enc_tile_w, g.k_h > 0 ? (int)kColSecond : (int)kColMain, 0, g.n, -1, t, g.k_h, g.enc_real, 0);
     if (p.use_viewdirs && t == p.n_gemm - 1) {
       // the narrow heads: dW_head[c][k] = sum_p d_raw[p][c] X[p][k] with the activation tile on the M side
       add(0, t, g.n, (int)kColHead0, 0, p.h[1].k, 1, t, 0, 16, 1);                               // fc_rgb reads this layer's output
@@ -172,18 +178,19 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
   float* s_dgrad = reinterpret_cast<float*>(sm + mp.dgrad);
   float* s_encd = reinterpret_cast<float*>(sm + mp.encd);
   uint32_t* s_max = reinterpret_cast<uint32_t*>(sm + mp.misc);      // [2]: tile max of |d_raw| (alternating tiles)
+  float* s_us = reinterpret_cast<float*>(sm + mp.misc) + 2;         // [2]: the tile's unscale factor, for the drain
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + mp.bars);
   uint64_t* w_full = bars;                      // [kMaxWStages]
   uint64_t* w_empty = bars + kMaxWStages;       // [kMaxWStages]
-  uint64_t* bar_a = bars + 2 * kMaxWStages;     // chain A operand written (and chain accumulator drained)
-  uint64_t* bar_acc = bar_a + 1;                // chain MMA complete
-  uint64_t* bar_g = bar_acc + 1;                // G tile (+ indicator tile) written
+  uint64_t* bar_acc = bars + 2 * kMaxWStages;   // chain MMA complete
+  uint64_t* bar_g = bar_acc + 1;                // G tile (+ indicator tile) written, chain accumulator drained
   uint64_t* xh_full = bar_g + 1;
   uint64_t* xl_full = xh_full + 1;
   uint64_t* xh_free = xl_full + 1;
   uint64_t* xl_free = xh_free + 1;
-  uint64_t* job_done = xl_free + 1;             // [kMaxJobs]: job i of the running event complete
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(job_done + kMaxJobs);
+  uint64_t* job_done = xl_free + 1;             // [2][kMaxJobs]: job i of a layer of that parity complete
+  uint64_t* acc_free = job_done + 2 * kMaxJobs; // [2]: the drain is done with the accumulators of that parity
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(acc_free + 2);
   const uint32_t n_stages = (uint32_t)mp.n_stages;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -197,14 +204,15 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
       mbar_init(&w_full[i], 1);
       mbar_init(&w_empty[i], 1);
     }
-    mbar_init(bar_a, kEpi);
     mbar_init(bar_acc, 1);
     mbar_init(bar_g, kEpi);
     mbar_init(xh_full, 1);
     mbar_init(xl_full, 1);
     mbar_init(xh_free, 1);
     mbar_init(xl_free, 1);
-    for (int i = 0; i < kMaxJobs; ++i) mbar_init(&job_done[i], 1);
+    for (int i = 0; i < 2 * kMaxJobs; ++i) mbar_init(&job_done[i], 1);
+    mbar_init(&acc_free[0], kDrainThreads);
+    mbar_init(&acc_free[1], kDrainThreads);
     fence_barrier_init();
     s_max[0] = s_max[1] = 0u;
   }
@@ -228,6 +236,10 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
 
   const int my_tiles = (n_tiles > blockIdx.x) ? (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
 
+  // 512 threads start with 128 registers each; the epilogue warpgroups take what the others give back
+  // (setmaxnreg sits at the top of each role's branch so that the register allocator sees the role's budget)
+  if (warp >= 8 && warp < kDrainWarp0) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   if (warp == 9) {
     // ===================== weight producer: the chain MMA of event e streams layer t's transposed copies ============
     if (lane == 0) {
@@ -275,31 +287,38 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
   } else if (warp == 8) {
     // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
     Pipe pp;
-    uint32_t a_ph = 0, g_ph = 0, x_ph = 0;
-    const uint32_t t_acc = tmem + kColAcc, t_ahi = tmem + kColAhi, t_alo = tmem + kColAlo;
-    const uint32_t gh = smem_u32(sG), gl = gh + 32768, xh = smem_u32(sX), xl = xh + 32768, ind = smem_u32(sInd);
-    const uint32_t dh = smem_u32(sD), dl = dh + kIndBytes;
+    uint32_t g_ph = 0, x_ph = 0, gev = 0;  // gev: layers processed so far (selects the accumulator buffer)
+    uint32_t free_ph[2] = {0u, 0u};
+    const uint32_t t_acc = tmem + kColAcc;
+    // every descriptor is built ONCE; the loops only advance start-address fields (tc_common.cuh desc_adv)
+    const uint64_t g_hi_k = make_desc(smem_u32(sG), 128, 2048), g_lo_k = desc_adv(g_hi_k, 32768);    // K-major view (chain A)
+    const uint64_t g_hi_m = make_desc(smem_u32(sG), 2048, 128), g_lo_m = desc_adv(g_hi_m, 32768);    // MN-major view (job A)
+    const uint64_t ind_d = make_desc(smem_u32(sInd), 256, 128);
+    const uint64_t d_hi_d = make_desc(smem_u32(sD), 256, 128), d_lo_d = desc_adv(d_hi_d, kIndBytes);
+    const uint32_t x_hi_a = smem_u32(sX), x_lo_a = x_hi_a + 32768;
     for (int it = 0; it < my_tiles; ++it)
-      for (int e = 0; e < E; ++e) {
+      for (int e = 0; e < E; ++e, ++gev) {
         const GemmLayer& g = p.g[E - 1 - e];
+        PROF_SCOPE(10, mbar_wait(bar_g, g_ph));
+        g_ph ^= 1;
+        tc_fence_after();
         if (e + 1 < E) {
-          // ---- chain: accumulator[p][k] = 2^11 sum_n G_t[p][n] W_t[n][k], N = k_h, K = n
+          // ---- chain: accumulator[p][k] = 2^11 sum_n G_t[p][n] W_t[n][k], N = k_h, K = n; A = the G tile's K-major
+          // view (rows = points: SBO 16 * 128; K = features: LBO 128; one k-step = 2 feature blocks = 256 bytes)
           const uint32_t idesc = make_idesc_f16(g.k_h);
           const uint32_t slab_b = 16u * (uint32_t)g.k_h;
-          PROF_SCOPE(8, mbar_wait(bar_a, a_ph));
-          a_ph ^= 1;
-          tc_fence_after();
+          const uint64_t b_ring = make_desc(smem_u32(sm + mp.ring), slab_b, 128);
           for (int ks = 0; ks < (g.n >> 4); ++ks) {
             PROF_SCOPE(9, mbar_wait(&w_full[pp.stage], pp.phase));
             tc_fence_after();
-            const uint32_t wb = smem_u32(sm + mp.ring + pp.stage * kWStage);
             if (elect_one()) {
-              const uint64_t b_hs = make_desc(wb, slab_b, 128);
-              const uint64_t b_h = make_desc(wb + 2 * slab_b, slab_b, 128);
-              const uint64_t b_l = make_desc(wb + 4 * slab_b, slab_b, 128);
-              mma_ts_f16(t_acc, t_ahi + 8 * ks, b_hs, idesc, ks > 0 ? 1u : 0u);
-              mma_ts_f16(t_acc, t_alo + 8 * ks, b_h, idesc, 1u);
-              mma_ts_f16(t_acc, t_ahi + 8 * ks, b_l, idesc, 1u);
+              const uint64_t b_hs = desc_adv(b_ring, pp.stage * (uint32_t)kWStage);
+              const uint64_t b_h = desc_adv(b_hs, 2 * slab_b);
+              const uint64_t b_l = desc_adv(b_hs, 4 * slab_b);
+              const uint64_t a_hi = desc_adv(g_hi_k, ks * 256), a_lo = desc_adv(g_lo_k, ks * 256);
+              mma_ss_f16(t_acc, a_hi, b_hs, idesc, ks > 0 ? 1u : 0u);
+              mma_ss_f16(t_acc, a_lo, b_h, idesc, 1u);
+              mma_ss_f16(t_acc, a_hi, b_l, idesc, 1u);
               mma_commit(&w_empty[pp.stage]);
             }
             __syncwarp();
@@ -307,20 +326,20 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
           }
           if (elect_one()) mma_commit(bar_acc);
           __syncwarp();
-        } else {  // the last event of a tile (layer 0) has no chain MMA; keep bar_a's phase in step
-          mbar_wait(bar_a, a_ph);
-          a_ph ^= 1;
         }
-        // ---- weight-gradient jobs of this event
-        PROF_SCOPE(10, mbar_wait(bar_g, g_ph));
-        g_ph ^= 1;
-        tc_fence_after();
+        // ---- weight-gradient jobs of this event; the accumulators of this parity were last used two layers ago
+        if (gev >= 2) {
+          PROF_SCOPE(13, mbar_wait(&acc_free[gev & 1u], free_ph[gev & 1u]));
+          free_ph[gev & 1u] ^= 1;
+          tc_fence_after();
+        }
         const int nj = bp.n_jobs[e];
         for (int i = 0; i < nj; ++i) {
           const BwdJob& jq = bp.jobs[e][i];
           const int w = jq.n_b;
           const uint32_t fstr = (uint32_t)(w >> 3) * 128u;  // bytes between 8-point blocks of the activation tile
-          const uint32_t d = tmem + (uint32_t)jq.col;
+          const uint32_t d = tmem + (uint32_t)jq.col + (jq.dbuf ? (gev & 1u) * kMainStride : 0u);
+          const uint64_t x_hi_d = make_desc(x_hi_a, fstr, 128), x_lo_d = make_desc(x_lo_a, fstr, 128);  // MN-major views
           if (jq.kind == 1) {
             // head job: A = activation tile (rows = its features: SBO 128, K = points: LBO fstr), B = d_raw tile (N = 16)
             const uint32_t id16 = make_idesc_f16_mn(16, 1, 1);
@@ -329,7 +348,7 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
             if (elect_one()) {
 #pragma unroll
               for (int ks = 0; ks < 8; ++ks)
-                mma_ss_f16(d, make_desc(xl + ks * 2 * fstr, fstr, 128), make_desc(dh + ks * 512, 256, 128), id16, ks > 0 ? 1u : 0u);
+                mma_ss_f16(d, desc_adv(x_lo_d, ks * 2 * fstr), desc_adv(d_hi_d, ks * 512), id16, ks > 0 ? 1u : 0u);
               mma_commit(xl_free);
             }
             __syncwarp();
@@ -339,13 +358,13 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
             if (elect_one()) {
 #pragma unroll
               for (int ks = 0; ks < 8; ++ks)
-                mma_ss_f16(d, make_desc(xh + ks * 2 * fstr, fstr, 128), make_desc(dl + ks * 512, 256, 128), id16, 1u);
-              mma_ss_f16_scale11(d, make_desc(xh, fstr, 128), make_desc(dh, 256, 128), id16);
+                mma_ss_f16(d, desc_adv(x_hi_d, ks * 2 * fstr), desc_adv(d_lo_d, ks * 512), id16, 1u);
+              mma_ss_f16_scale11(d, x_hi_d, d_hi_d, id16);
 #pragma unroll
               for (int ks = 1; ks < 8; ++ks)
-                mma_ss_f16(d, make_desc(xh + ks * 2 * fstr, fstr, 128), make_desc(dh + ks * 512, 256, 128), id16, 1u);
+                mma_ss_f16(d, desc_adv(x_hi_d, ks * 2 * fstr), desc_adv(d_hi_d, ks * 512), id16, 1u);
               mma_commit(xh_free);
-              mma_commit(&job_done[i]);
+              mma_commit(&job_done[(gev & 1u) * kMaxJobs + i]);
             }
             __syncwarp();
             continue;
@@ -357,8 +376,7 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
           if (elect_one()) {
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks)
-              mma_ss_f16(d, make_desc(gh + ks * 4096, 2048, 128), make_desc(xl + ks * 2 * fstr, fstr, 128), id_mn,
-                         ks > 0 ? 1u : 0u);
+              mma_ss_f16(d, desc_adv(g_hi_m, ks * 4096), desc_adv(x_lo_d, ks * 2 * fstr), id_mn, ks > 0 ? 1u : 0u);
             mma_commit(xl_free);
           }
           __syncwarp();
@@ -368,94 +386,90 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
           if (elect_one()) {
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks)
-              mma_ss_f16(d, make_desc(gl + ks * 4096, 2048, 128), make_desc(xh + ks * 2 * fstr, fstr, 128), id_mn, 1u);
-            mma_ss_f16_scale11(d, make_desc(gh, 2048, 128), make_desc(xh, fstr, 128), id_mn);
+              mma_ss_f16(d, desc_adv(g_lo_m, ks * 4096), desc_adv(x_hi_d, ks * 2 * fstr), id_mn, 1u);
+            mma_ss_f16_scale11(d, g_hi_m, x_hi_d, id_mn);
 #pragma unroll
             for (int ks = 1; ks < 8; ++ks)
-              mma_ss_f16(d, make_desc(gh + ks * 4096, 2048, 128), make_desc(xh + ks * 2 * fstr, fstr, 128), id_mn, 1u);
+              mma_ss_f16(d, desc_adv(g_hi_m, ks * 4096), desc_adv(x_hi_d, ks * 2 * fstr), id_mn, 1u);
             mma_commit(xh_free);
             if (i == 0) {
               // indicator job: sums[n][j] = sum over the points of ray j of the tile of G[p][n] (16 columns)
               const uint32_t id16 = make_idesc_f16_mn(16, 1, 1);
-              const uint32_t di = tmem + kColInd;
+              const uint32_t di = d + kIndOff;
 #pragma unroll
               for (int ks = 0; ks < 8; ++ks)
-                mma_ss_f16(di, make_desc(gl + ks * 4096, 2048, 128), make_desc(ind + ks * 512, 256, 128), id16,
-                           ks > 0 ? 1u : 0u);
-              mma_ss_f16_scale11(di, make_desc(gh, 2048, 128), make_desc(ind, 256, 128), id16);
+                mma_ss_f16(di, desc_adv(g_lo_m, ks * 4096), desc_adv(ind_d, ks * 512), id16, ks > 0 ? 1u : 0u);
+              mma_ss_f16_scale11(di, g_hi_m, ind_d, id16);
 #pragma unroll
               for (int ks = 1; ks < 8; ++ks)
-                mma_ss_f16(di, make_desc(gh + ks * 4096, 2048, 128), make_desc(ind + ks * 512, 256, 128), id16, 1u);
+                mma_ss_f16(di, desc_adv(g_hi_m, ks * 4096), desc_adv(ind_d, ks * 512), id16, 1u);
             }
-            mma_commit(&job_done[i]);
+            mma_commit(&job_done[(gev & 1u) * kMaxJobs + i]);
           }
           __syncwarp();
         }
       }
-  } else {
-    // ===================== epilogue warps =====================
-    const int row = tid & 127, half = tid >> 7;
+  }
+  } else if (warp >= kDrainWarp0) {
+    // ===================== drain warps: thread = accumulator row (tensor-memory lane) =====================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+    const int row = tid - kDrainWarp0 * 32;
     const uint32_t lane_base = ((uint32_t)((warp & 3) * 32)) << 16;
-    const uint32_t t_acc = tmem + lane_base + kColAcc;
-    const uint32_t t_ahi = tmem + lane_base + kColAhi, t_alo = tmem + lane_base + kColAlo;
-    float* stg = reinterpret_cast<float*>(sm + mp.stg + half * 2 * kStgBytes);
-    uint32_t stg_n = 0;  // chunks this half has staged so far (selects the buffer)
-    uint32_t acc_ph = 0, job_ph[kMaxJobs] = {0u, 0u, 0u};
-    // previous event: what has to be drained before this event's G tile may be written
-    int prev_e = -1;
-    float prev_unscale = 0.f;
-    int prev_nrays = 0;
-
-    // drain the accumulators of event `de` (scale `us`): weight blocks -> gradient blob, indicator sums -> bias /
-    // direction-encoding accumulators in shared memory
-    auto drain_event = [&](const int de, const float us, const int n_rays_tile) {
-      const int nj = bp.n_jobs[de];
-      const int t = E - 1 - de;
-      const GemmLayer& g = p.g[t];
-      for (int i = 0; i < nj; ++i) {
-        PROF_SCOPE(3, mbar_wait(&job_done[i], job_ph[i]));
-        job_ph[i] ^= 1;
-        tc_fence_after();
-        const BwdJob& j = bp.jobs[de][i];
-        if (j.kind == 1) {
-          // head job: lane = input feature k of the head, columns = d_raw channels: dW_head[c][k], a handful of atomics
-          if (half == 0) {
+    float* stg = reinterpret_cast<float*>(sm + mp.stg);
+    uint32_t stg_n = 0, gev = 0;  // chunks staged so far (selects one of the four staging buffers); layers drained
+    uint32_t job_ph[2][kMaxJobs] = {{0u, 0u, 0u}, {0u, 0u, 0u}};
+    for (int it = 0; it < my_tiles; ++it) {
+      const int64_t tile = blockIdx.x + (int64_t)it * gridDim.x;
+      const int64_t p0 = tile * kTileRows;
+      const int64_t last_pt = (p0 + kTileRows - 1 < P) ? p0 + kTileRows - 1 : P - 1;
+      const int n_rays_tile = (int)(last_pt / S - p0 / S) + 1;
+      for (int de = 0; de < E; ++de, ++gev) {
+        const uint32_t parity = gev & 1u;
+        const int nj = bp.n_jobs[de];
+        const GemmLayer& g = p.g[E - 1 - de];
+        for (int i = 0; i < nj; ++i) {
+          PROF_SCOPE(3, mbar_wait(&job_done[parity * kMaxJobs + i], job_ph[parity][i]));
+          job_ph[parity][i] ^= 1;
+          tc_fence_after();
+          const float us = s_us[it & 1];  // written by the epilogue before this tile's first job could be issued
+          const BwdJob& j = bp.jobs[de][i];
+          const uint32_t jcol = (uint32_t)j.col + (j.dbuf ? parity * kMainStride : 0u);
+          if (j.kind == 1) {
+            // head job: lane = input feature k of the head, columns = d_raw channels: dW_head[c][k], a handful of atomics
             uint32_t v16[16];
-            tmem_ld16(tmem + lane_base + (uint32_t)j.col, v16);
+            tmem_ld16(tmem + lane_base + jcol, v16);
             tmem_wait_ld();
             const HeadLayer& h = p.h[j.dst_head];
             if (row < h.k)
               for (int c = 0; c < h.n_out; ++c)
                 atomicAdd(flat_grad + h.flat_w + (size_t)c * h.k + row, __uint_as_float(v16[(h.out_col + c) & 15]) * us);
+            continue;
           }
-          continue;
-        }
-        // 16-column chunks, alternating between the two halves; each half alternates between its two staging buffers
-        // and only waits for the bulk reduction issued two chunks ago before overwriting a buffer
-        const int nchunk = j.n_b >> 4;
-        for (int c = half; c < nchunk; c += 2) {
-          uint32_t v[16];
-          tmem_ld16(tmem + lane_base + (uint32_t)j.col + 16 * c, v);
-          float* sb = stg + (stg_n & 1u) * (kStgBytes / 4);
-          if (row == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // buffer (stg_n & 1) is free again
-          bar_half(half);
-          tmem_wait_ld();
+          // 16-column chunks through four rotating staging buffers: a buffer is rewritten only after the bulk
+          // reduction issued four chunks ago has finished reading it
+          const int nchunk = j.n_b >> 4;
+          for (int c = 0; c < nchunk; ++c) {
+            uint32_t v[16];
+            tmem_ld16(tmem + lane_base + jcol + 16 * c, v);
+            float* sb = stg + (stg_n & 3u) * (kStgBytes / 4);
+            if (row == 0) asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory");
+            bar_half(0);
+            tmem_wait_ld();
 #pragma unroll
-          for (int q = 0; q < 4; ++q)
-            *reinterpret_cast<float4*>(sb + row * 16 + ((q ^ ((row >> 1) & 3)) << 2)) =
-                make_float4(__uint_as_float(v[4 * q]) * us, __uint_as_float(v[4 * q + 1]) * us,
-                            __uint_as_float(v[4 * q + 2]) * us, __uint_as_float(v[4 * q + 3]) * us);
-          fence_proxy_async();
-          bar_half(half);
-          if (row == 0)
-            bulk_reduce_add_f32(gblob + j.gb_off + (size_t)c * 2048 + j.row0 * 16, sb + j.row0 * 16, (uint32_t)j.nrows * 64u);
-          ++stg_n;
-        }
-        if (i == 0) {
-          // indicator sums of this event: bias gradient (all rays) and, for layers_dir[0], the direction-encoding part
-          if (half == 0) {
+            for (int q = 0; q < 4; ++q)
+              *reinterpret_cast<float4*>(sb + row * 16 + ((q ^ ((row >> 1) & 3)) << 2)) =
+                  make_float4(__uint_as_float(v[4 * q]) * us, __uint_as_float(v[4 * q + 1]) * us,
+                              __uint_as_float(v[4 * q + 2]) * us, __uint_as_float(v[4 * q + 3]) * us);
+            fence_proxy_async();
+            bar_half(0);
+            if (row == 0)
+              bulk_reduce_add_f32(gblob + j.gb_off + (size_t)c * 2048 + j.row0 * 16, sb + j.row0 * 16, (uint32_t)j.nrows * 64u);
+            ++stg_n;
+          }
+          if (i == 0) {
+            // indicator sums of this layer: bias gradient (all rays) and, for layers_dir[0], the direction-encoding part
             uint32_t v16[16];
-            tmem_ld16(tmem + lane_base + kColInd, v16);
+            tmem_ld16(tmem + lane_base + jcol + kIndOff, v16);
             tmem_wait_ld();
             float tot = 0.f;
 #pragma unroll
@@ -475,8 +489,42 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
             }
           }
         }
+        tc_fence_before();
+        mbar_arrive(&acc_free[parity]);
       }
-      tc_fence_before();
+    }
+    if (row == 0) bulk_wait_all();
+    bar_half(0);
+    // ---- flush the bias / direction-encoding accumulators of this CTA
+    for (int gi = 0; gi < p.n_gemm; ++gi)
+      for (int i = row; i < p.g[gi].n; i += kDrainThreads) atomicAdd(flat_grad + p.g[gi].flat_b + i, s_bgrad[p.g[gi].cum_n + i]);
+    if (p.use_viewdirs) {
+      const GemmLayer& gd = p.g[p.n_gemm - 1];
+      const int in_real = gd.k_h + gd.enc_real;
+      for (int i = row; i < gd.n * p.dim_dir; i += kDrainThreads) {
+        const int n = i / p.dim_dir, k = i - n * p.dim_dir;
+        atomicAdd(flat_grad + gd.flat_w + (size_t)n * in_real + gd.k_h + k, s_dgrad[n * 28 + k]);
+      }
+      if (row < 3) atomicAdd(flat_grad + p.h[1].flat_b + row, s_bgrad[p.enc_cum[0] + row]);
+      if (row == 3) atomicAdd(flat_grad + p.h[0].flat_b, s_bgrad[p.enc_cum[0] + 3]);
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 192;");
+    const int row = tid & 127, half = tid >> 7;
+    const uint32_t lane_base = ((uint32_t)((warp & 3) * 32)) << 16;
+    const uint32_t t_acc = tmem + lane_base + kColAcc;
+    uint32_t acc_ph = 0, gev = 0;  // gev: layers processed so far (parity of the job barriers)
+    uint32_t job_ph[2][kMaxJobs] = {{0u, 0u, 0u}, {0u, 0u, 0u}};
+    int prev_e = -1;  // the previous layer: its jobs must have finished reading the G tile before this layer's is written
+
+    auto wait_jobs = [&](const int de, const uint32_t parity) {  // every job of that layer complete
+      const int nj = bp.n_jobs[de];
+      for (int i = 0; i < nj; ++i) {
+        PROF_SCOPE(3, mbar_wait(&job_done[parity * kMaxJobs + i], job_ph[parity][i]));
+        job_ph[parity][i] ^= 1;
+      }
+      tc_fence_after();
     };
 
     for (int it = 0; it < my_tiles; ++it) {
@@ -504,12 +552,12 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
       const float sc = scaled ? __uint_as_float((256u - ex) << 23) : 1.f;
       const float unscale = (scaled ? __uint_as_float((ex - 2u) << 23) : 1.f) * kActInv;  // activations are stored / 16
       const float dr[4] = {d4.x * sc, d4.y * sc, d4.z * sc, d4.w * sc};
+      if (tid == 0) s_us[it & 1] = unscale;
 
       for (int e = 0; e < E; ++e) {
         const int t = E - 1 - e;
         const GemmLayer& g = p.g[t];
         const bool has_mma = e >= 1;
-        const bool has_next = e + 1 < E;
         int hsel = -1;
         if (p.h[0].src == t) hsel = 0;
         if (p.n_head > 1 && p.h[1].src == t) hsel = 1;
@@ -572,26 +620,18 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
                 const float y1 = (mword & (2u << q)) ? y[q + 1] : 0.f;
                 split_f16x2(y0, y1, hi[ch][q >> 1], lo[ch][q >> 1]);
               }
-              if (has_next) {
-                tmem_st16(t_ahi + c0 / 2, hi[ch]);
-                tmem_st16(t_alo + c0 / 2, lo[ch]);
-              }
             }
           }
         }
-        if (has_next) tmem_wait_st();
         tc_fence_before();
-        mbar_arrive(bar_a);
-
-        // ---------------- drain the previous event's jobs (they ran under part A) ----------------
 #ifdef NERFB200_PROF
         const long long _tb = clock64();
         if (tid == 0 && blockIdx.x == 0) g_prof[1] += (unsigned long long)(_tb - _ta);
 #endif
-        if (prev_e >= 0) drain_event(prev_e, prev_unscale, prev_nrays);
+        // the previous layer's jobs read the G tile: they must be complete before it is overwritten
+        if (prev_e >= 0) wait_jobs(prev_e, (gev - 1u) & 1u);
 #ifdef NERFB200_PROF
         const long long _tc = clock64();
-        if (tid == 0 && blockIdx.x == 0) g_prof[2] += (unsigned long long)(_tc - _tb);
 #endif
 
         // ---------------- part B: the held registers -> G tile (MN-major A operand of this event's jobs) ----------------
@@ -661,28 +701,12 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
         fence_proxy_async();
         mbar_arrive(bar_g);
 #ifdef NERFB200_PROF
-        if (tid == 0 && blockIdx.x == 0) { g_prof[5] += (unsigned long long)(clock64() - _tc); g_prof[7] += 1; }
+        const long long _td2 = clock64();
+        if (tid == 0 && blockIdx.x == 0) { g_prof[5] += (unsigned long long)(_td2 - _tc); g_prof[7] += 1; }
 #endif
         prev_e = e;
-        prev_unscale = unscale;
-        prev_nrays = n_rays_tile;
+        ++gev;
       }
-    }
-    if (prev_e >= 0) drain_event(prev_e, prev_unscale, prev_nrays);
-    if (row == 0) bulk_wait_all();
-    epi_bar256();
-    // ---- flush the bias / direction-encoding accumulators of this CTA
-    for (int gi = 0; gi < p.n_gemm; ++gi)
-      for (int i = tid; i < p.g[gi].n; i += kEpi) atomicAdd(flat_grad + p.g[gi].flat_b + i, s_bgrad[p.g[gi].cum_n + i]);
-    if (p.use_viewdirs) {
-      const GemmLayer& gd = p.g[p.n_gemm - 1];
-      const int in_real = gd.k_h + gd.enc_real;
-      for (int i = tid; i < gd.n * p.dim_dir; i += kEpi) {
-        const int n = i / p.dim_dir, k = i - n * p.dim_dir;
-        atomicAdd(flat_grad + gd.flat_w + (size_t)n * in_real + gd.k_h + k, s_dgrad[n * 28 + k]);
-      }
-      if (tid < 3) atomicAdd(flat_grad + p.h[1].flat_b + tid, s_bgrad[p.enc_cum[0] + tid]);
-      if (tid == 3) atomicAdd(flat_grad + p.h[0].flat_b, s_bgrad[p.enc_cum[0] + 3]);
     }
   }
 

@@ -73,6 +73,13 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) |
          (1ull << 46);
 }
+// Advance a descriptor's 14-bit start-address field by `bytes` with ONE 32-bit add.  The MMA issue loops must stay
+// lean: the issuing thread runs alone, every dependent integer instruction costs it ~5 cycles, and rebuilding 64-bit
+// descriptors per instruction made an MMA cost ~80-115 cycles of issue time against 64 on the tensor pipe
+// (tools/mma_rate.cu; with precomputed descriptors all flavours run at the nominal N / 2 cycles).
+__device__ __forceinline__ uint64_t desc_adv(uint64_t d, uint32_t bytes) {
+  return (d & 0xFFFFFFFF00000000ull) | (uint64_t)((uint32_t)d + (bytes >> 4));
+}
 // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, M = 128
 __device__ __forceinline__ uint32_t make_idesc(int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);

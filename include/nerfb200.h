@@ -97,6 +97,21 @@ int32_t nerfb200_sample_coarse(const float* rays, int32_t ray_stride, int64_t n_
                                const float* t_rand, int32_t n_coarse, int32_t perturb, int32_t lindisp,
                                float* z, void* stream);
 
+/* Ray generation / packing in one launch.  Output rows of `out_stride` floats:
+ *   11: [o(3) d(3) near far viewdir(3)]  (train_utils.py:164-168, use_viewdirs)   8: without the view direction
+ *    6: [o(3) d(3)] only (get_ray_bundle, nerf_helpers.py:67-110)
+ * ndc != 0 applies ndc_rays(H, W, focal, 1.0, ...) (nerf_helpers.py:170-197) AFTER the view directions were taken
+ * from the original directions (train_utils.py:143-160).
+ * gen_rays:  c2w12 = the 3 x 4 camera-to-world matrix, 12 floats in HOST memory; pixel_ids[n] (device, int64,
+ *            j * width + i) or NULL for all height*width pixels in row-major order.
+ * pack_rays: caller-supplied origins / directions ro, rd [n][3] (device), the reference call shape. */
+int32_t nerfb200_gen_rays(const float* c2w12_host, int32_t height, int32_t width, float focal, const int64_t* pixel_ids,
+                          int64_t n, int32_t ndc, float near, float far, int32_t use_viewdirs, int32_t out_stride,
+                          float* out, void* stream);
+int32_t nerfb200_pack_rays(const float* ro, const float* rd, int64_t n, int32_t height, int32_t width, float focal,
+                           int32_t ndc, float near, float far, int32_t use_viewdirs, int32_t out_stride, float* out,
+                           void* stream);
+
 /* positional_encoding (nerf_helpers.py:113-157) of x[n][3] -> out[n][dim], dim = 3*include + 6*n_freq.
  * which = 0: xyz encoder of `arch`, 1: direction encoder. */
 int32_t nerfb200_encode(const nerfb200_arch_t* arch, int32_t which, const float* x, int64_t n, float* out,
@@ -186,13 +201,15 @@ int32_t nerfb200_render_fwd(const nerfb200_arch_t* arch_c, const nerfb200_arch_t
                             int32_t training, int32_t impl, void* stream);
 
 /* Backward of render_fwd: g_coarse/g_fine[n][8] upstream grads (g_fine NULL when no fine pass);
- * accumulates into flat_grad_c / flat_grad_f (may alias different ranges of one buffer). */
+ * accumulates into flat_grad_c / flat_grad_f (may alias different ranges of one buffer).
+ * parts: bit 0 = the fine network's backward, bit 1 = the coarse network's (3 = both, fine first).  Two calls (1, then
+ * 2) let the host start the all-reduce of the fine network's gradient while the coarse backward runs. */
 int32_t nerfb200_render_bwd(const nerfb200_arch_t* arch_c, const nerfb200_arch_t* arch_f,
                             const nerfb200_render_opts_t* opts, const float* blob_c, const float* blob_f,
                             const float* rays, int32_t ray_stride, int64_t n_rays, const float* noise_c,
                             const float* noise_f, const float* g_coarse, const float* g_fine,
                             void* workspace, float* flat_grad_c, float* flat_grad_f, int32_t impl,
-                            void* stream);
+                            int32_t parts, void* stream);
 
 /* Fused Adam over a flat vector (torch.optim.Adam semantics, train_nerf.py:136-141,261-270):
  * p, m, v updated in place from g; step is the 1-based step count AFTER this update; grad_scale

@@ -63,6 +63,8 @@ SIGNATURES = {
     "nerfb200_flat_layout": (I32, [AP, I32, C.POINTER(I64), C.POINTER(I64), C.POINTER(I32), C.POINTER(I32)]),
     "nerfb200_pack_weights": (I32, [AP, P, P, P]),
     "nerfb200_sample_coarse": (I32, [P, I32, I64, P, P, I32, I32, I32, P, P]),
+    "nerfb200_gen_rays": (I32, [C.POINTER(F32), I32, I32, F32, P, I64, I32, F32, F32, I32, I32, P, P]),
+    "nerfb200_pack_rays": (I32, [P, P, I64, I32, I32, F32, I32, F32, F32, I32, I32, P, P]),
     "nerfb200_encode": (I32, [AP, I32, P, I64, P, P]),
     "nerfb200_stash_floats": (I64, [AP, I64]),
     "nerfb200_mlp_fwd": (I32, [AP, P, P, I32, P, I64, I32, P, P, I32, P]),
@@ -76,7 +78,7 @@ SIGNATURES = {
     "nerfb200_render_workspace_bytes": (I64, [AP, AP, OP, I64, I32]),
     "nerfb200_render_workspace_layout": (I32, [AP, AP, OP, I64, I32, C.POINTER(I64)]),
     "nerfb200_render_fwd": (I32, [AP, AP, OP, P, P, P, I32, I64, P, P, P, P, I32, P, P, P, P, I32, I32, P]),
-    "nerfb200_render_bwd": (I32, [AP, AP, OP, P, P, P, I32, I64, P, P, P, P, P, P, P, I32, P]),
+    "nerfb200_render_bwd": (I32, [AP, AP, OP, P, P, P, I32, I64, P, P, P, P, P, P, P, I32, I32, P]),
     "nerfb200_adam_step": (I32, [P, P, P, P, I64, I32, F32, F32, F32, F32, F32, P]),
 }
 

@@ -352,6 +352,28 @@ int32_t nerfb200_sample_coarse(const float* rays, int32_t ray_stride, int64_t n_
                               lindisp, z, static_cast<cudaStream_t>(stream));
 }
 
+int32_t nerfb200_gen_rays(const float* c2w12_host, int32_t height, int32_t width, float focal, const int64_t* pixel_ids,
+                          int64_t n, int32_t ndc, float near, float far, int32_t use_viewdirs, int32_t out_stride,
+                          float* out, void* stream) {
+  if (!c2w12_host || !out || n <= 0) {
+    set_error("gen_rays: null pointer or empty batch");
+    return NERFB200_ERR_INVALID;
+  }
+  return launch_gen_rays(c2w12_host, height, width, focal, pixel_ids, n, ndc, near, far, use_viewdirs, out_stride, out,
+                         static_cast<cudaStream_t>(stream));
+}
+
+int32_t nerfb200_pack_rays(const float* ro, const float* rd, int64_t n, int32_t height, int32_t width, float focal,
+                           int32_t ndc, float near, float far, int32_t use_viewdirs, int32_t out_stride, float* out,
+                           void* stream) {
+  if (!ro || !rd || !out || n <= 0) {
+    set_error("pack_rays: null pointer or empty batch");
+    return NERFB200_ERR_INVALID;
+  }
+  return launch_pack_rays(ro, rd, n, height, width, focal, ndc, near, far, use_viewdirs, out_stride, out,
+                          static_cast<cudaStream_t>(stream));
+}
+
 int32_t nerfb200_encode(const nerfb200_arch_t* arch, int32_t which, const float* x, int64_t n, float* out,
                         void* stream) {
   Plan p;
@@ -565,7 +587,7 @@ int32_t nerfb200_render_bwd(const nerfb200_arch_t* arch_c, const nerfb200_arch_t
                             const nerfb200_render_opts_t* opts, const float* blob_c, const float* blob_f,
                             const float* rays, int32_t ray_stride, int64_t n_rays, const float* noise_c,
                             const float* noise_f, const float* g_coarse, const float* g_fine, void* workspace,
-                            float* flat_grad_c, float* flat_grad_f, int32_t impl, void* stream) {
+                            float* flat_grad_c, float* flat_grad_f, int32_t impl, int32_t parts, void* stream) {
   Plan pc, pf;
   NB_TRY(build_plan(arch_c, &pc));
   NB_TRY(check_opts(opts));
@@ -588,12 +610,17 @@ int32_t nerfb200_render_bwd(const nerfb200_arch_t* arch_c, const nerfb200_arch_t
   auto F = [&](int64_t off) { return reinterpret_cast<float*>(base + off); };
   const int nc = opts->n_coarse, ns = opts->n_coarse + opts->n_fine;
 
-  if (fine) {
+  if ((parts & 3) == 0) {
+    set_error("render_bwd: parts must select the fine (1) and / or the coarse (2) backward");
+    return NERFB200_ERR_INVALID;
+  }
+  if (fine && (parts & 1)) {
     NB_TRY(launch_composite_bwd(F(w.raw_f), F(w.z_f), rays, ray_stride, opts->noise_std > 0.f ? noise_f : nullptr,
                                 g_fine, n_rays, ns, opts->noise_std, opts->white_bkgd, F(w.d_raw), s));
     NB_TRY(launch_mlp_bwd(pf, blob_f, rays, ray_stride, F(w.z_f), n_rays, ns, F(w.d_raw), F(w.stash_f), F(w.gstash),
                           flat_grad_f, impl, s));
   }
+  if (!(parts & 2)) return NERFB200_OK;
   // the coarse weights feed the resampler only through a detach (train_utils.py:103), so the
   // coarse net's gradient comes from rgb/disp/acc_coarse alone.
   NB_TRY(launch_composite_bwd(F(w.raw_c), F(w.z_c), rays, ray_stride, opts->noise_std > 0.f ? noise_c : nullptr,

@@ -81,6 +81,10 @@ void count_launch();  // one call per kernel launched (nerfb200_launch_count)
 int launch_pack(const Plan& p, const float* flat, float* blob, cudaStream_t s);
 int launch_sample_coarse(const float* rays, int ray_stride, int64_t n_rays, const float* t_vals,
                          const float* t_rand, int n_coarse, int perturb, int lindisp, float* z, cudaStream_t s);
+int launch_gen_rays(const float* c2w12_host, int height, int width, float focal, const int64_t* pix, int64_t n, int ndc,
+                    float near, float far, int use_viewdirs, int out_stride, float* out, cudaStream_t s);
+int launch_pack_rays(const float* ro, const float* rd, int64_t n, int height, int width, float focal, int ndc, float near,
+                     float far, int use_viewdirs, int out_stride, float* out, cudaStream_t s);
 int launch_encode(const Plan& p, int which, const float* x, int64_t n, float* out, cudaStream_t s);
 int launch_mlp_fwd_simt(const Plan& p, const float* blob, const float* rays, int ray_stride, const float* z,
                         int64_t n_rays, int n_samples, float* raw, float* stash, cudaStream_t s);

@@ -143,10 +143,14 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int c0, 
   for (int j = 0; j < 32; j += 4) {
     float y[4];
     const float4 b = *reinterpret_cast<const float4*>(a.bias + c0 + j);
-    y[0] = fmaxf(fmaf(__uint_as_float(v[j]), kLoInv, b.x), a.lb);
-    y[1] = fmaxf(fmaf(__uint_as_float(v[j + 1]), kLoInv, b.y), a.lb);
-    y[2] = fmaxf(fmaf(__uint_as_float(v[j + 2]), kLoInv, b.z), a.lb);
-    y[3] = fmaxf(fmaf(__uint_as_float(v[j + 3]), kLoInv, b.w), a.lb);
+    // NaN-propagating ReLU (fmaxf would turn the NaN of an out-of-range operand into a plausible 0): an activation or
+    // weight beyond the fp16 x 2 range must surface as a non-finite output, never as a silently wrong finite one
+    const float t0 = fmaf(__uint_as_float(v[j]), kLoInv, b.x), t1 = fmaf(__uint_as_float(v[j + 1]), kLoInv, b.y);
+    const float t2 = fmaf(__uint_as_float(v[j + 2]), kLoInv, b.z), t3 = fmaf(__uint_as_float(v[j + 3]), kLoInv, b.w);
+    y[0] = t0 < a.lb ? a.lb : t0;
+    y[1] = t1 < a.lb ? a.lb : t1;
+    y[2] = t2 < a.lb ? a.lb : t2;
+    y[3] = t3 < a.lb ? a.lb : t3;
 #pragma unroll
     for (int c = 0; c < kHN; ++c) {
       const float4 w = *reinterpret_cast<const float4*>(a.hw + c * a.hk + c0 + j);

@@ -23,7 +23,7 @@ def _ptr(t: Optional[torch.Tensor]):
         return None
     if not t.is_cuda:
         raise RuntimeError("nerfb200: tensor is not on a CUDA device (there is no CPU path)")
-    if t.dtype not in (torch.float32, torch.int32, torch.uint8):
+    if t.dtype not in (torch.float32, torch.int32, torch.int64, torch.uint8):
         raise RuntimeError(f"nerfb200: unsupported dtype {t.dtype}")
     if not t.is_contiguous():
         raise RuntimeError("nerfb200: tensor must be contiguous")
@@ -167,6 +167,36 @@ def sample_coarse(rays, t_vals, t_rand, n_coarse, perturb, lindisp):
                                           n_coarse, int(bool(perturb)), int(bool(lindisp)), _ptr(z), _stream()),
                "sample_coarse")
     return z
+
+
+def gen_rays(c2w, height, width, focal, pixel_ids, device, ndc=False, near=0.0, far=1.0, use_viewdirs=True, stride=None):
+    """Rays of the given pixels (int64 ids j * W + i on `device`, or None for the whole image) of a pinhole camera with
+    camera-to-world matrix ``c2w`` (anything convertible to 12+ host floats: the top 3 x 4 block is used)."""
+    lib = _lib.load()
+    m = torch.as_tensor(c2w, dtype=torch.float32, device="cpu").reshape(-1, 4)[:3].contiguous().reshape(-1)
+    c12 = (C.c_float * 12)(*m.tolist())
+    n = int(pixel_ids.numel()) if pixel_ids is not None else int(height) * int(width)
+    if stride is None:
+        stride = 11 if use_viewdirs else 8
+    out = torch.empty(n, stride, dtype=torch.float32, device=device)
+    _lib.check(lib.nerfb200_gen_rays(c12, int(height), int(width), float(focal), _ptr(pixel_ids), n, int(bool(ndc)),
+                                     float(near), float(far), int(bool(use_viewdirs) and stride == 11), stride, _ptr(out),
+                                     _stream()), "gen_rays")
+    return out
+
+
+def pack_rays(ro, rd, height, width, focal, ndc, near, far, use_viewdirs, stride=None):
+    """[o d near far (viewdir)] rows from caller-supplied origins / directions (train_utils.py:143-168);
+    stride 6 returns [o d] only (ndc_rays)."""
+    lib = _lib.load()
+    n = ro.shape[0]
+    if stride is None:
+        stride = 11 if use_viewdirs else 8
+    out = torch.empty(n, stride, dtype=torch.float32, device=ro.device)
+    _lib.check(lib.nerfb200_pack_rays(_ptr(ro), _ptr(rd), n, int(height), int(width), float(focal), int(bool(ndc)),
+                                      float(near), float(far), int(bool(use_viewdirs)), stride, _ptr(out), _stream()),
+               "pack_rays")
+    return out
 
 
 def encode(arch: ArchSpec, which: int, x: torch.Tensor) -> torch.Tensor:
@@ -331,7 +361,7 @@ def render_fwd(arch_c, arch_f, opts: RenderOpts, blob_c, blob_f, rays, t_vals, t
 
 
 def render_bwd(arch_c, arch_f, opts: RenderOpts, blob_c, blob_f, rays, noise_c, noise_f, g_c, g_f, workspace,
-               flat_grad_c, flat_grad_f, impl: int = IMPL_SIMT):
+               flat_grad_c, flat_grad_f, impl: int = IMPL_SIMT, parts: int = 3):
     lib = _lib.load()
     fine = opts.n_fine > 0
     ac = arch_c.c_struct()
@@ -340,4 +370,4 @@ def render_bwd(arch_c, arch_f, opts: RenderOpts, blob_c, blob_f, rays, noise_c, 
                                        _ptr(blob_c), _ptr(blob_f) if fine else None, _ptr(rays), rays.shape[1],
                                        rays.shape[0], _ptr(noise_c), _ptr(noise_f) if fine else None, _ptr(g_c),
                                        _ptr(g_f) if fine else None, _ptr(workspace), _ptr(flat_grad_c),
-                                       _ptr(flat_grad_f) if fine else None, impl, _stream()), "render_bwd")
+                                       _ptr(flat_grad_f) if fine else None, impl, int(parts), _stream()), "render_bwd")

@@ -33,7 +33,9 @@ def init_distributed(backend: Optional[str] = None):
 
 
 def enable_gradient_sync(group=None):
-    """Average parameter gradients across ranks inside the render backward (one all-reduce)."""
+    """Average parameter gradients across ranks: inside the render backward when the step renders ONE chunk of rays
+    (two halves of one all-reduce, the fine network's overlapped with the coarse backward); for multi-chunk steps the
+    chunks' gradients are summed first and ``sync_gradients`` / ``FusedAdam.step`` all-reduce them once."""
     if dist.is_initialized() and dist.get_world_size(group) > 1:
         train_utils._GRAD_SYNC = (group, dist.get_world_size(group))
     else:
@@ -42,6 +44,26 @@ def enable_gradient_sync(group=None):
 
 def disable_gradient_sync():
     train_utils._GRAD_SYNC = None
+    train_utils._PENDING_SYNC = False
+
+
+def sync_gradients(params) -> bool:
+    """All-reduce (average) the ``.grad`` of ``params`` once if a multi-chunk backward left them unsynchronised.
+    Optimizers other than FusedAdam call this between ``loss.backward()`` and ``optimizer.step()``."""
+    if not train_utils._PENDING_SYNC or train_utils._GRAD_SYNC is None:
+        train_utils._PENDING_SYNC = False
+        return False
+    group, world = train_utils._GRAD_SYNC
+    grads = [p.grad for p in params if p.grad is not None]
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    flat.mul_(1.0 / world)
+    off = 0
+    for g in grads:
+        g.copy_(flat[off:off + g.numel()].view_as(g))
+        off += g.numel()
+    train_utils._PENDING_SYNC = False
+    return True
 
 
 def shard_bounds(n_total: int, rank: int, world: int):
@@ -86,8 +108,9 @@ def flatten_parameters(model, arch: ops.ArchSpec) -> torch.Tensor:
 
 class FusedAdam:
     """torch.optim.Adam semantics (train_nerf.py:136-141) over flat buffers, one kernel per model,
-    with the reference's exponential LR schedule folded in (train_nerf.py:264-270):
-    lr_i = lr0 * decay_factor ** (i / (lr_decay * 1000))."""
+    with the reference's exponential LR schedule folded in (train_nerf.py:264-270).  The reference sets
+    lr = lr0 * decay_factor ** (i / (lr_decay * 1000)) AFTER optimizer.step() of iteration i, so the step of iteration
+    i runs with the rate computed at iteration i - 1 (iterations 0 and 1 both use lr0): reproduced here."""
 
     def __init__(self, models_and_archs: Iterable, lr=5e-3, betas=(0.9, 0.999), eps=1e-8, lr_decay: Optional[float] = None,
                  lr_decay_factor: float = 0.1):
@@ -104,7 +127,7 @@ class FusedAdam:
     def current_lr(self):
         if self.lr_decay is None:
             return self.lr0
-        return self.lr0 * (self.lr_decay_factor ** (self.step_count / (self.lr_decay * 1000.0)))
+        return self.lr0 * (self.lr_decay_factor ** (max(self.step_count - 1, 0) / (self.lr_decay * 1000.0)))
 
     def zero_grad(self):
         for it in self.items:
@@ -115,6 +138,8 @@ class FusedAdam:
     def step(self, grad_scale: float = 1.0):
         lr = self.current_lr()
         self.step_count += 1
+        if train_utils._PENDING_SYNC:  # multi-chunk step: one all-reduce over everything, now
+            sync_gradients([p for it in self.items for p in it["params"]])
         for it in self.items:
             params = it["params"]
             g0 = params[0].grad

@@ -20,7 +20,7 @@ from typing import Optional
 import torch
 
 from . import ops
-from .nerf_helpers import Embedder, get_minibatches, ndc_rays
+from .nerf_helpers import Embedder, get_minibatches
 
 # The reference does not forward ``mode`` to predict_and_render_radiance (train_utils.py:171-181),
 # so validation renders use options.nerf.train.* for sampling/noise.  True reproduces that.
@@ -37,6 +37,9 @@ def _auto_impl(arch_c, arch_f, n_coarse, n_fine):
 
 # gradient synchronisation across ranks: (process_group, world_size) or None; see parallel.py
 _GRAD_SYNC = None
+# set when a step rendered its rays in several chunks: their gradients are summed by autograd first and
+# all-reduced ONCE afterwards (parallel.sync_gradients / FusedAdam.step), never once per chunk
+_PENDING_SYNC = False
 
 
 def set_default_impl(impl):
@@ -178,7 +181,7 @@ def _packed(model, arch: ops.ArchSpec):
 class _RenderChunk(torch.autograd.Function):
     @staticmethod
     def forward(ctx, cfg, rays, t_vals, t_rand, noise_c, u, noise_f, *params):
-        arch_c, arch_f, opts, blob_c, blob_f, training, impl, n_pc = cfg
+        arch_c, arch_f, opts, blob_c, blob_f, training, impl, n_chunks = cfg
         out_c, out_f, ws = ops.render_fwd(arch_c, arch_f, opts, blob_c, blob_f, rays, t_vals, t_rand, noise_c, u,
                                           noise_f, training=training, impl=impl)
         if training:
@@ -192,7 +195,7 @@ class _RenderChunk(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_c, g_f):
-        arch_c, arch_f, opts, blob_c, blob_f, training, impl, n_pc = ctx.cfg
+        arch_c, arch_f, opts, blob_c, blob_f, training, impl, n_chunks = ctx.cfg
         rays, noise_c, noise_f = ctx.saved_tensors
         fine = opts.n_fine > 0
         n = rays.shape[0]
@@ -203,17 +206,35 @@ class _RenderChunk(torch.autograd.Function):
         nc = arch_c.flat_param_count()
         nf = arch_f.flat_param_count() if fine else 0
         flat_grad = torch.zeros(nc + nf, dtype=torch.float32, device=rays.device)
-        ops.render_bwd(arch_c, arch_f, opts, blob_c, blob_f, rays, noise_c, noise_f, g_c.contiguous(),
-                       g_f.contiguous() if fine else None, ctx.ws, flat_grad[:nc], flat_grad[nc:] if fine else None,
-                       impl=impl)
-        ctx.ws = None
-        if _GRAD_SYNC is not None:
-            # the ONE collective of a data-parallel step: both nets' gradients in one flat buffer
+        g_c = g_c.contiguous()
+        g_f = g_f.contiguous() if fine else None
+        args = (arch_c, arch_f, opts, blob_c, blob_f, rays, noise_c, noise_f, g_c, g_f, ctx.ws, flat_grad[:nc],
+                flat_grad[nc:] if fine else None)
+        sync = _GRAD_SYNC
+        if sync is not None and n_chunks != 1:
+            # several chunks per step: no collective here (ranks may even differ in their chunk counts); the summed
+            # gradients are all-reduced once by parallel.sync_gradients / FusedAdam.step
+            global _PENDING_SYNC
+            _PENDING_SYNC = True
+            sync = None
+        if sync is None:
+            ops.render_bwd(*args, impl=impl)
+        else:
+            # the ONE collective of a data-parallel step, split in two so that the fine network's half (final as soon
+            # as its backward is done) crosses NVLink while the coarse network's backward is still running
             import torch.distributed as dist
 
-            group, world = _GRAD_SYNC
-            dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=group)
+            group, world = sync
+            works = []
+            if fine:
+                ops.render_bwd(*args, impl=impl, parts=1)
+                works.append(dist.all_reduce(flat_grad[nc:], op=dist.ReduceOp.SUM, group=group, async_op=True))
+            ops.render_bwd(*args, impl=impl, parts=2 if fine else 3)
+            works.append(dist.all_reduce(flat_grad[:nc], op=dist.ReduceOp.SUM, group=group, async_op=True))
+            for w in works:
+                w.wait()
             flat_grad.mul_(1.0 / world)
+        ctx.ws = None
         grads = []
         for arch, base in ((arch_c, 0),) + (((arch_f, nc),) if fine else ()):
             for _, w_off, b_off, fin, fout in arch.flat_layout():
@@ -236,6 +257,7 @@ def predict_and_render_radiance(
     *,
     randoms: Optional[dict] = None,
     impl: Optional[int] = None,
+    _n_chunks: int = 1,
 ):
     """nerf/train_utils.py:28-127 for one chunk of packed rays ``[o d near far (viewdir)]``.
 
@@ -289,7 +311,7 @@ def predict_and_render_radiance(
         impl = DEFAULT_IMPL
     if impl is None:
         impl = _auto_impl(arch_c, arch_f, nc, nf)
-    cfg = (arch_c, arch_f, opts, blob_c, blob_f, training, int(impl), len(params_c))
+    cfg = (arch_c, arch_f, opts, blob_c, blob_f, training, int(impl), int(_n_chunks))
     out_c, out_f = _RenderChunk.apply(cfg, rays, t_vals, t_rand, noise_c, u, noise_f, *all_params)
     rgb_c, disp_c, acc_c = out_c[:, :3], out_c[:, 3], out_c[:, 4]
     if out_f is None:
@@ -316,25 +338,56 @@ def run_one_iter_of_nerf(
     """nerf/train_utils.py:130-202: ray packing (viewdirs, optional NDC, near/far), chunking by
     ``options.nerf.<mode>.chunksize``, per-chunk render, concatenation and -- in "validation" mode --
     the reshape back to image shape."""
-    viewdirs = None
-    if options.nerf.use_viewdirs:
-        viewdirs = ray_directions
-        viewdirs = viewdirs / viewdirs.norm(p=2, dim=-1).unsqueeze(-1)
-        viewdirs = viewdirs.view((-1, 3))
+    use_viewdirs = bool(options.nerf.use_viewdirs)
     restore_shapes = [ray_directions.shape, ray_directions.shape[:-1], ray_directions.shape[:-1]]
     if model_fine:
         restore_shapes += restore_shapes
-    if options.dataset.no_ndc is False:
-        ro, rd = ndc_rays(height, width, focal_length, 1.0, ray_origins, ray_directions)
-        ro, rd = ro.view((-1, 3)), rd.view((-1, 3))
-    else:
-        ro, rd = ray_origins.view((-1, 3)), ray_directions.view((-1, 3))
-    near = options.dataset.near * torch.ones_like(rd[..., :1])
-    far = options.dataset.far * torch.ones_like(rd[..., :1])
-    rays = torch.cat((ro, rd, near, far), dim=-1)
-    if options.nerf.use_viewdirs:
-        rays = torch.cat((rays, viewdirs), dim=-1)
+    if not ray_directions.is_cuda:
+        raise NotImplementedError("nerfb200: rays must be on a CUDA device (there is no CPU path)")
+    # view directions (from the pre-NDC directions), optional NDC warp, near / far columns and the row layout
+    # [o d near far viewdir]: one kernel (csrc/raygen.cu), same op order as the reference's chain of torch ops
+    rays = ops.pack_rays(ray_origins.reshape(-1, 3).float().contiguous(), ray_directions.reshape(-1, 3).float().contiguous(),
+                         height, width, focal_length, options.dataset.no_ndc is False, options.dataset.near,
+                         options.dataset.far, use_viewdirs)
 
+    return _render_packed(rays, restore_shapes, model_coarse, model_fine, options, mode, encode_position_fn,
+                          encode_direction_fn, randoms, impl)
+
+
+def run_one_iter_of_nerf_from_pose(
+    height,
+    width,
+    focal_length,
+    model_coarse,
+    model_fine,
+    tform_cam2world,
+    pixel_ids,
+    options,
+    mode="train",
+    encode_position_fn=None,
+    encode_direction_fn=None,
+    *,
+    randoms: Optional[dict] = None,
+    impl: Optional[int] = None,
+):
+    """``run_one_iter_of_nerf`` for callers that hold a pose and pixel ids instead of ray tensors:
+    the reference's training loop builds ALL H*W rays of the image with get_ray_bundle and then indexes the few
+    thousand it samples (train_nerf.py:196-226); here the rays of exactly those pixels are generated on the device
+    (csrc/raygen.cu) in the packed layout the render kernels read.  ``pixel_ids``: int64, ``j * width + i``, on the
+    target device (None = the whole image, returned image-shaped in "validation" mode)."""
+    dev = pixel_ids.device if pixel_ids is not None else next(model_coarse.parameters()).device
+    use_viewdirs = bool(options.nerf.use_viewdirs)
+    rays = ops.gen_rays(tform_cam2world, height, width, focal_length, pixel_ids, dev, ndc=options.dataset.no_ndc is False,
+                        near=options.dataset.near, far=options.dataset.far, use_viewdirs=use_viewdirs)
+    lead = (height, width) if pixel_ids is None else tuple(pixel_ids.shape)
+    restore_shapes = [lead + (3,), lead, lead] * (2 if model_fine else 1)
+    return _render_packed(rays, restore_shapes, model_coarse, model_fine, options, mode, encode_position_fn,
+                          encode_direction_fn, randoms, impl)
+
+
+def _render_packed(rays, restore_shapes, model_coarse, model_fine, options, mode, encode_position_fn, encode_direction_fn,
+                   randoms, impl):
+    """Chunking, per-chunk render, concatenation and the validation reshape of train_utils.py:170-202."""
     batches = get_minibatches(rays, chunksize=getattr(options.nerf, mode).chunksize)
     if randoms is not None and len(batches) != 1:
         raise ValueError("injected randoms require a single ray chunk")
@@ -344,7 +397,7 @@ def run_one_iter_of_nerf(
             batch, model_coarse, model_fine, options, mode=inner_mode,
             encode_position_fn=encode_position_fn,
             encode_direction_fn=encode_direction_fn if options.nerf.use_viewdirs else None,
-            randoms=randoms, impl=impl,
+            randoms=randoms, impl=impl, _n_chunks=len(batches),
         )
         for batch in batches
     ]

@@ -38,7 +38,26 @@ def _worker(rank, world, port, ret):
     g_shard = grads(slice(lo, hi), sync=True)        # all-reduced inside backward
     g_full = grads(slice(0, n), sync=False)          # single-GPU global batch
     rel = ((g_shard - g_full).norm() / g_full.norm()).item()
-    ret[rank] = rel
+
+    # coarse + fine networks: the fine half of the all-reduce is issued before the coarse backward runs
+    c2 = Case("lego_a0_train")
+    n2 = c2.ro.shape[0]
+
+    def grads2(rows, sync):
+        (parallel.enable_gradient_sync if sync else parallel.disable_gradient_sync)()
+        mc, mf, epf, edf = build_models(c2)
+        rnd = {k: v[rows].cuda() for k, v in c2.randoms.items()}
+        out = nb.run_one_iter_of_nerf(c2.H, c2.W, c2.focal, mc, mf, c2.ro[rows].cuda(), c2.rd[rows].cuda(), c2.options,
+                                      encode_position_fn=epf, encode_direction_fn=edf, randoms=rnd)
+        tgt = c2.target[rows].cuda()
+        (torch.nn.functional.mse_loss(out[0], tgt) + torch.nn.functional.mse_loss(out[3], tgt)).backward()
+        return torch.cat([p.grad.reshape(-1) for p in list(mc.parameters()) + list(mf.parameters())])
+
+    lo2, hi2 = parallel.shard_bounds(n2, rank, world)
+    g2_shard = grads2(slice(lo2, hi2), sync=True)
+    g2_full = grads2(slice(0, n2), sync=False)
+    rel2 = ((g2_shard - g2_full).norm() / g2_full.norm()).item()
+    ret[rank] = max(rel, rel2)
     dist.barrier()
     dist.destroy_process_group()
 

@@ -61,3 +61,38 @@ def test_two_rank_gradient_allreduce_equals_global_batch():
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
     assert dict(ret) == {0: True, 1: True}
+
+
+def _worker_sync(rank, world, port, ret):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    torch.set_num_threads(1)
+    from nerf_pytorch_b200 import parallel, train_utils
+
+    parallel.init_distributed(backend="gloo")
+    parallel.enable_gradient_sync()
+    # a multi-chunk backward leaves the summed per-chunk gradients unsynchronised and raises the flag; ONE all-reduce
+    # over everything follows (never one per chunk: ranks may differ in their chunk counts)
+    params = [torch.nn.Parameter(torch.zeros(3, 4)), torch.nn.Parameter(torch.zeros(5))]
+    for i, p in enumerate(params):
+        p.grad = torch.full_like(p, float(rank + 1 + 10 * i))
+    ok = parallel.sync_gradients(params) is False          # nothing pending: no collective, gradients untouched
+    ok = ok and float(params[0].grad[0, 0]) == rank + 1
+    train_utils._PENDING_SYNC = True
+    ok = ok and parallel.sync_gradients(params) is True
+    want0, want1 = (1 + 2) / 2.0, (11 + 12) / 2.0
+    ok = ok and torch.allclose(params[0].grad, torch.full((3, 4), want0)) and torch.allclose(params[1].grad, torch.full((5,), want1))
+    ok = ok and train_utils._PENDING_SYNC is False
+    ret[rank] = bool(ok)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_multi_chunk_gradients_are_all_reduced_once():
+    world = 2
+    port = 31500 + (os.getpid() % 2000)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker_sync, args=(world, port, ret), nprocs=world, join=True)
+    assert dict(ret) == {0: True, 1: True}

@@ -68,25 +68,32 @@ __host__ __device__ inline SmemMap smem_map(const Plan& p) {
 
 // The fixed interleaving of the two slots' events.  A tile is E = n_gemm + 1 events: event 0 = prologue (encodings),
 // event e = epilogue of layer e - 1; it is followed by MMA #e = layer e (e < n_gemm) whose A operand it wrote.
-struct Seq {
-  int E, off1, n0, n1, ticks;
-  __device__ __forceinline__ Seq(int events, int my_tiles) {
-    E = events;
-    off1 = events >> 1;
-    n0 = (my_tiles + 1) >> 1;
-    n1 = my_tiles >> 1;
-    const int t0 = n0 * E, t1 = n1 > 0 ? off1 + n1 * E : 0;
-    ticks = t0 > t1 ? t0 : t1;
-  }
-  // event of slot s at tick tk: returns false if there is none; j = the slot's tile counter, e = event in the tile
-  __device__ __forceinline__ bool at(int tk, int s, int& j, int& e) const {
-    const int idx = tk - (s ? off1 : 0);
-    if (idx < 0) return false;
-    j = idx / E;
-    e = idx - j * E;
-    return j < (s ? n1 : n0);
+// Every role walks the same sequence of half-ticks h = 0, 1, 2, ...: slot h & 1 at tick h >> 1; slot 1 starts E / 2
+// ticks after slot 0.  A Cursor is one slot's position; the roles keep the two cursors in registers and swap them
+// after every half-tick (no division, no dynamically indexed state).
+struct Cursor {
+  int idx, j, e, n;  // idx: ticks since the slot's start (negative: not started); tile counter; event; tiles of the slot
+  __device__ __forceinline__ bool active() const { return idx >= 0 && j < n; }
+  __device__ __forceinline__ void next(int E) {
+    if (idx >= 0 && ++e == E) { e = 0; ++j; }
+    ++idx;
   }
 };
+struct Seq {
+  int E, half_ticks;
+  Cursor c0, c1;
+  __device__ __forceinline__ Seq(int events, int my_tiles) {
+    E = events;
+    const int off1 = events >> 1;
+    const int n0 = (my_tiles + 1) >> 1, n1 = my_tiles >> 1;
+    const int t0 = n0 * E, t1 = n1 > 0 ? off1 + n1 * E : 0;
+    half_ticks = 2 * (t0 > t1 ? t0 : t1);
+    c0.idx = 0; c0.j = 0; c0.e = 0; c0.n = n0;
+    c1.idx = -off1; c1.j = 0; c1.e = 0; c1.n = n1;
+  }
+};
+template <typename T>
+__device__ __forceinline__ void swap2(T& a, T& b) { const T t = a; a = b; b = t; }
 
 // what MMA #e (= layer e) contracts: weights, shapes
 struct MmaInfo {
@@ -118,16 +125,17 @@ struct TileState {
 
 using namespace tc;
 
-// One 32-column chunk of one row in the epilogue (the hot loop), specialised at compile time on the number of
-// narrow-head rows reading this layer (kHN: 0, 1, 3, 4) and on training outputs (kTrain):
+// One 32-column chunk of one row in the epilogue (the hot loop; ONE instance per kernel: the code must stay inside the
+// instruction cache -- the four head-count specialisations of the previous version, each inlined at two call sites of
+// two slot copies, made the kernel 160 KB and 10 % of the issue slots were instruction-fetch stalls):
 //   ys = max(acc * 2^-11 + bias/16, lb) = activation / 16      (lb = 0 with ReLU, -inf without; the bias already
-//   holds the per-ray direction term for layers_dir[0]); head rows accumulate ys * (16 w);
+//   holds the per-ray direction term for layers_dir[0]); head rows accumulate ys * (16 w) in a separate short pass;
 // then -> fp16 hi / lo -> tensor memory (next layer's A operand) and, in training, the stash tile.
 struct ChunkArgs {
   const float* bias;      // this layer's bias / 16 (or the per-ray bias of layers_dir[0])
   float lb;               // ReLU lower bound
   const float* hw;        // head weights [hn][hk] in smem (pre-multiplied by 16)
-  int hk;
+  int hk, hn;
   uint32_t* mword_out;    // train: where to store the ReLU mask word (or nullptr when the row is out of range)
   uint8_t* stash_hi;      // train: this row's first 16-byte piece of the layer's stash tile (hi block), feature block 0
   int stash_lo_off;       // train: byte offset of the lo block
@@ -135,35 +143,40 @@ struct ChunkArgs {
   bool has_next;
 };
 
-template <int kHN, bool kTrain>
+template <bool kTrain>
 __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int c0, const ChunkArgs& a, float (&hacc)[4]) {
   float x[32];
-  uint32_t bits = 0;
 #pragma unroll
   for (int j = 0; j < 32; j += 4) {
-    float y[4];
     const float4 b = *reinterpret_cast<const float4*>(a.bias + c0 + j);
-    // NaN-propagating ReLU (fmaxf would turn the NaN of an out-of-range operand into a plausible 0): an activation or
-    // weight beyond the fp16 x 2 range must surface as a non-finite output, never as a silently wrong finite one
-    const float t0 = fmaf(__uint_as_float(v[j]), kLoInv, b.x), t1 = fmaf(__uint_as_float(v[j + 1]), kLoInv, b.y);
-    const float t2 = fmaf(__uint_as_float(v[j + 2]), kLoInv, b.z), t3 = fmaf(__uint_as_float(v[j + 3]), kLoInv, b.w);
-    y[0] = t0 < a.lb ? a.lb : t0;
-    y[1] = t1 < a.lb ? a.lb : t1;
-    y[2] = t2 < a.lb ? a.lb : t2;
-    y[3] = t3 < a.lb ? a.lb : t3;
-#pragma unroll
-    for (int c = 0; c < kHN; ++c) {
-      const float4 w = *reinterpret_cast<const float4*>(a.hw + c * a.hk + c0 + j);
-      hacc[c] = fmaf(y[0], w.x, fmaf(y[1], w.y, fmaf(y[2], w.z, fmaf(y[3], w.w, hacc[c]))));
-    }
-    if (kTrain) {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) bits |= (y[q] > 0.f ? 1u : 0u) << (j + q);
-    }
-#pragma unroll
-    for (int q = 0; q < 4; ++q) x[j + q] = y[q];
+    // NaN-propagating ReLU: an activation or weight beyond the fp16 x 2 range must surface as a non-finite output,
+    // never as a silently wrong finite one
+    x[j] = fmax_nan(fmaf(__uint_as_float(v[j]), kLoInv, b.x), a.lb);
+    x[j + 1] = fmax_nan(fmaf(__uint_as_float(v[j + 1]), kLoInv, b.y), a.lb);
+    x[j + 2] = fmax_nan(fmaf(__uint_as_float(v[j + 2]), kLoInv, b.z), a.lb);
+    x[j + 3] = fmax_nan(fmaf(__uint_as_float(v[j + 3]), kLoInv, b.w), a.lb);
   }
-  if (kTrain && a.mword_out) *a.mword_out = bits;
+  if (a.hn > 0) {  // narrow heads reading this layer (2 of the 9 layers): register dot products
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      if (c < a.hn) {
+        const float4* w4 = reinterpret_cast<const float4*>(a.hw + c * a.hk + c0);
+        float acc = hacc[c];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 w = w4[j];
+          acc = fmaf(x[4 * j], w.x, fmaf(x[4 * j + 1], w.y, fmaf(x[4 * j + 2], w.z, fmaf(x[4 * j + 3], w.w, acc))));
+        }
+        hacc[c] = acc;
+      }
+    }
+  }
+  if (kTrain && a.mword_out) {
+    uint32_t bits = 0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) bits |= (x[j] > 0.f ? 1u : 0u) << j;
+    *a.mword_out = bits;
+  }
   if (a.has_next || kTrain) {
     // fp16 x 2: two K-adjacent values per tensor-memory column / per 32-bit word of a stash piece
     uint32_t hi[16], lo[16];
@@ -186,17 +199,6 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int c0, 
   }
 }
 
-template <bool kTrain>
-__device__ __forceinline__ void epilogue_chunk_dispatch(int hn, const uint32_t (&v)[32], int c0, const ChunkArgs& a,
-                                                        float (&hacc)[4]) {
-  switch (hn) {
-    case 0: epilogue_chunk<0, kTrain>(v, c0, a, hacc); break;
-    case 1: epilogue_chunk<1, kTrain>(v, c0, a, hacc); break;
-    case 3: epilogue_chunk<3, kTrain>(v, c0, a, hacc); break;
-    default: epilogue_chunk<4, kTrain>(v, c0, a, hacc); break;
-  }
-}
-
 // kTrain: the forward also writes the activation stash (operand tiles + ReLU bit masks + the encoding tile).
 template <bool kTrain>
 __global__ void __launch_bounds__(kThreadsTc, 1)
@@ -213,15 +215,16 @@ mlp_fwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
   float* s_encd = reinterpret_cast<float*>(sm + mp.encd);
   float* s_hpart = reinterpret_cast<float*>(sm + mp.hpart);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + mp.bars);
-  uint64_t* bar_full = bars;                      // [kMaxStages]  weights landed
-  uint64_t* bar_empty = bars + kMaxStages;        // [kMaxStages]  stage consumed by the MMAs
+  // barrier addresses are kept as 32-bit shared-memory addresses (8 bytes per barrier)
+  const uint32_t bar_full = smem_u32(bars);                // [kMaxStages]  weights landed
+  const uint32_t bar_empty = bar_full + 8 * kMaxStages;    // [kMaxStages]  stage consumed by the MMAs
   // per slot: A operand columns [0,64) of the next MMA ready AND the accumulator fully drained into registers
   // (bar_a1), columns [64,128) ready (bar_a2): the MMA's first four k-steps only need the former, so they run
   // while the epilogue is still working on the second half of its columns.  bar_acc: accumulator complete.
-  uint64_t* bar_a1 = bars + 2 * kMaxStages;       // [2]
-  uint64_t* bar_a2 = bar_a1 + 2;                  // [2]
-  uint64_t* bar_acc = bar_a2 + 2;                 // [2]
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_acc + 2);
+  const uint32_t bar_a1 = bar_empty + 8 * kMaxStages;      // [2]
+  const uint32_t bar_a2 = bar_a1 + 16;                     // [2]
+  const uint32_t bar_acc = bar_a2 + 16;                    // [2]
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 6);
   const uint32_t n_stages = (uint32_t)mp.n_stages;
 
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -231,13 +234,13 @@ mlp_fwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
 
   if (tid == 0) {
     for (int i = 0; i < kMaxStages; ++i) {
-      mbar_init(&bar_full[i], 1);
-      mbar_init(&bar_empty[i], 1);
+      mbar_init(&bars[i], 1);
+      mbar_init(&bars[kMaxStages + i], 1);
     }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&bar_a1[s], kEpiThreads);
-      mbar_init(&bar_a2[s], kEpiThreads);
-      mbar_init(&bar_acc[s], 1);
+      mbar_init(&bars[2 * kMaxStages + s], kEpiThreads);
+      mbar_init(&bars[2 * kMaxStages + 2 + s], kEpiThreads);
+      mbar_init(&bars[2 * kMaxStages + 4 + s], 1);
     }
     fence_barrier_init();
   }
@@ -266,65 +269,66 @@ mlp_fwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
   const int E = p.n_gemm + 1;
   const int nM = E - 1;
   const Seq seq(E, my_tiles);
+  const uint32_t ring_a = smem_u32(sm + mp.ring);
 
   if (warp == 9) {
     // ===================== weight producer =====================
     if ((tid & 31) == 0) {
       Pipe pp;
       const uint64_t pol = l2_policy_evict_last();
-      for (int tk = 0; tk < seq.ticks; ++tk) {
-        for (int s = 0; s < 2; ++s) {
-          int j, e;
-          if (!seq.at(tk, s, j, e) || e >= nM) continue;
-          const MmaInfo mi = mma_info(p, blob, e);
+      Cursor cur = seq.c0, oth = seq.c1;
+      for (int h = 0; h < seq.half_ticks; ++h) {
+        if (cur.active() && cur.e < nM) {
+          const MmaInfo mi = mma_info(p, blob, cur.e);
           for (int ks = 0; ks < mi.ksteps; ks += kStepsPerStage) {
             const uint32_t bytes = (uint32_t)min(kStepsPerStage, mi.ksteps - ks) * mi.kbytes;
-            mbar_wait(&bar_empty[pp.stage], pp.phase ^ 1);
-            mbar_arrive_expect_tx(&bar_full[pp.stage], bytes);
-            bulk_g2s_hint(sm + mp.ring + pp.stage * kStageBytes, mi.src + (size_t)ks * mi.kbytes, bytes,
-                          &bar_full[pp.stage], pol);
+            mbar_wait(bar_empty + 8 * pp.stage, pp.phase ^ 1);
+            mbar_arrive_expect_tx(bar_full + 8 * pp.stage, bytes);
+            bulk_g2s_hint(ring_a + pp.stage * kStageBytes, mi.src + (size_t)ks * mi.kbytes, bytes,
+                          bar_full + 8 * pp.stage, pol);
             pp.advance(n_stages);
           }
         }
+        cur.next(E);
+        swap2(cur, oth);
       }
     }
   } else if (warp == 8) {
     // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
     Pipe pp;
-    uint32_t a_phase[2] = {0u, 0u};
-    for (int tk = 0; tk < seq.ticks; ++tk) {
-#pragma unroll
-      for (int s = 0; s < 2; ++s) {
-        int j, e;
-        if (!seq.at(tk, s, j, e) || e >= nM) continue;
-        const MmaInfo mi = mma_info(p, blob, e);
+    uint32_t a_ph = 0, a_ph_oth = 0;  // phase of this slot's bar_a1 / bar_a2 (swapped with the cursors)
+    Cursor cur = seq.c0, oth = seq.c1;
+    for (int h = 0; h < seq.half_ticks; ++h) {
+      if (cur.active() && cur.e < nM) {
+        const uint32_t s = (uint32_t)(h & 1);
+        const MmaInfo mi = mma_info(p, blob, cur.e);
         const uint32_t idesc = make_idesc_f16(mi.n_mma);
         const uint32_t slab_b = 16u * (uint32_t)mi.n_mma;  // bytes of one weight slab
         const uint32_t t_acc = tmem + s * kSlotCols + kColAcc;
         const uint32_t t_ahi = tmem + s * kSlotCols + kColAhi, t_alo = tmem + s * kSlotCols + kColAlo;
         // descriptors are built once per layer; the loops below only advance their start-address fields
-        const uint64_t b_ring = make_desc(smem_u32(sm + mp.ring), slab_b, 128);
-        const uint64_t e_hi_d0 = make_desc(smem_u32(sm + mp.enc + s * kEncBytes), 128, (uint32_t)(enc_w >> 3) * 128u);
+        const uint64_t b_ring = make_desc(ring_a, slab_b, 128);
+        const uint64_t e_hi_d0 = make_desc(smem_u32(sm + mp.enc) + s * kEncBytes, 128, (uint32_t)(enc_w >> 3) * 128u);
         const uint64_t e_lo_d0 = desc_adv(e_hi_d0, (uint32_t)enc_half);
         constexpr int kHalfSteps = 4;  // k-steps covered by A columns [0, 64)
-        mbar_wait(&bar_a1[s], a_phase[s]);
+        mbar_wait(bar_a1 + 8 * s, a_ph);
         tc_fence_after();
         bool second = false;  // bar_a2 of this MMA consumed?
         for (int ks0 = 0; ks0 < mi.ksteps; ks0 += kStepsPerStage) {
           if (!second && (ks0 + kStepsPerStage > kHalfSteps || mi.ksteps_h == 0)) {
-            mbar_wait(&bar_a2[s], a_phase[s]);  // this stage touches A columns >= 64 (or the encodings)
+            mbar_wait(bar_a2 + 8 * s, a_ph);  // this stage touches A columns >= 64 (or the encodings)
             tc_fence_after();
             second = true;
           }
-          mbar_wait(&bar_full[pp.stage], pp.phase);
+          mbar_wait(bar_full + 8 * pp.stage, pp.phase);
           tc_fence_after();
           const uint64_t b_st = desc_adv(b_ring, pp.stage * (uint32_t)kStageBytes);
           if (elect_one()) {
 #pragma unroll
-            for (int h = 0; h < kStepsPerStage; ++h) {
-              const int ks = ks0 + h;
+            for (int hh = 0; hh < kStepsPerStage; ++hh) {
+              const int ks = ks0 + hh;
               if (ks < mi.ksteps) {
-                const uint64_t b_hs = desc_adv(b_st, h * 6 * slab_b);
+                const uint64_t b_hs = desc_adv(b_st, hh * 6 * slab_b);
                 const uint64_t b_h = desc_adv(b_hs, 2 * slab_b);
                 const uint64_t b_l = desc_adv(b_hs, 4 * slab_b);
                 const uint32_t acc0 = ks > 0 ? 1u : 0u;
@@ -341,24 +345,29 @@ mlp_fwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
                 }
               }
             }
-            mma_commit(&bar_empty[pp.stage]);  // frees the ring stage once these MMAs have read it
+            mma_commit(bar_empty + 8 * pp.stage);  // frees the ring stage once these MMAs have read it
           }
           __syncwarp();
           pp.advance(n_stages);
         }
-        if (!second) mbar_wait(&bar_a2[s], a_phase[s]);  // keep the phases aligned for short layers
-        a_phase[s] ^= 1;
-        if (elect_one()) mma_commit(&bar_acc[s]);  // accumulator of this MMA complete
+        if (!second) mbar_wait(bar_a2 + 8 * s, a_ph);  // keep the phases aligned for short layers
+        a_ph ^= 1;
+        if (elect_one()) mma_commit(bar_acc + 8 * s);  // accumulator of this MMA complete
         __syncwarp();
       }
+      cur.next(E);
+      swap2(cur, oth);
+      swap2(a_ph, a_ph_oth);
     }
   } else {
     // ===================== prologue / epilogue warps =====================
     const int row = tid & 127, half = tid >> 7;
     const uint32_t lane_base = ((uint32_t)((warp & 3) * 32)) << 16;
-    TileState st0, st1;
+    TileState ts, ts_oth;   // this half-tick's slot and the other one (swapped with the cursors)
+    Cursor cur = seq.c0, oth = seq.c1;
 
-    auto run_event = [&](const int s, TileState& ts, const int j, const int e) {
+    // ONE instance of the event code serves both slots (slot = h & 1)
+    auto run_event = [&](const int s, const int j, const int e) {
       const uint32_t t_acc = tmem + lane_base + s * kSlotCols + kColAcc;
       const uint32_t t_ahi = tmem + lane_base + s * kSlotCols + kColAhi;
       const uint32_t t_alo = tmem + lane_base + s * kSlotCols + kColAlo;
@@ -434,8 +443,8 @@ mlp_fwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
         if (kTrain && tid == 0)  // the encoding tile goes to the stash as it is: one bulk store
           bulk_s2g(reinterpret_cast<uint8_t*>(stash + (size_t)P_pad * p.enc_cum[0]) + (size_t)ts.tile * tile_bytes(enc_w),
                    e_hi, (uint32_t)tile_bytes(enc_w));
-        mbar_arrive(&bar_a1[s]);
-        mbar_arrive(&bar_a2[s]);
+        mbar_arrive(bar_a1 + 8 * s);
+        mbar_arrive(bar_a2 + 8 * s);
         return;
       }
 
@@ -457,7 +466,7 @@ mlp_fwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
       if (kTrain && valid)
         mask_row = reinterpret_cast<uint32_t*>(stash) + (size_t)P_pad * (p.mask_base + g.mask_cum) + (size_t)pt * (g.n >> 5);
 
-      mbar_wait(&bar_acc[s], ts.acc_phase);
+      mbar_wait(bar_acc + 8 * s, ts.acc_phase);
       ts.acc_phase ^= 1;
       tc_fence_after();
 
@@ -465,7 +474,7 @@ mlp_fwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
         ChunkArgs ca;
         ca.bias = is_dir ? viewb + ts.ray_slot * 64 : s_bias + g.cum_n;
         ca.lb = g.relu ? 0.f : -3.4e38f;
-        ca.hw = hw; ca.hk = hk;
+        ca.hw = hw; ca.hk = hk; ca.hn = hn;
         ca.has_next = has_next;
         ca.stash_hi = nullptr;
         ca.stash_lo_off = tile_half_bytes(g.n);
@@ -484,17 +493,17 @@ mlp_fwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
         ca.mword_out = mask_row ? mask_row + (c0a >> 5) : nullptr;
         ca.tmem_hi = t_ahi + c0a / 2;  // two fp16 per tensor-memory column
         ca.tmem_lo = t_alo + c0a / 2;
-        epilogue_chunk_dispatch<kTrain>(hn, v0, c0a, ca, hacc);
+        epilogue_chunk<kTrain>(v0, c0a, ca, hacc);
         if (has_next) {
           tmem_wait_st();
           tc_fence_before();
-          mbar_arrive(&bar_a1[s]);
+          mbar_arrive(bar_a1 + 8 * s);
         }
         if (nch == 2) {
           ca.mword_out = mask_row ? mask_row + (c0b >> 5) : nullptr;
           ca.tmem_hi = t_ahi + c0b / 2;
           ca.tmem_lo = t_alo + c0b / 2;
-          epilogue_chunk_dispatch<kTrain>(hn, v1, c0b, ca, hacc);
+          epilogue_chunk<kTrain>(v1, c0b, ca, hacc);
         }
       }
 
@@ -503,7 +512,7 @@ mlp_fwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
       if (has_next) {
         tmem_wait_st();
         tc_fence_before();
-        mbar_arrive(&bar_a2[s]);
+        mbar_arrive(bar_a2 + 8 * s);
       } else {
         tc_fence_before();
       }
@@ -520,10 +529,12 @@ mlp_fwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
       }
     };
 
-    for (int tk = 0; tk < seq.ticks; ++tk) {
-      int j, e;
-      if (seq.at(tk, 0, j, e)) run_event(0, st0, j, e);
-      if (seq.at(tk, 1, j, e)) run_event(1, st1, j, e);
+#pragma unroll 1
+    for (int h = 0; h < seq.half_ticks; ++h) {
+      if (cur.active()) run_event(h & 1, cur.j, cur.e);
+      cur.next(E);
+      swap2(cur, oth);
+      swap2(ts, ts_oth);
     }
   }
 

@@ -182,12 +182,17 @@ def cpu_train_steps(arch, n_rays, steps, warmup, threads=None, device="cpu"):
     options = O.make_options(num_coarse=NC, num_fine=NF, perturb=True, radiance_field_noise_std=CFG["noise"],
                              near=CFG["near"], far=CFG["far"], no_ndc=not CFG["ndc"], chunksize=131072)
     times = []
+    import contextlib
+    # the port creates its helper tensors (t_vals, noise, frequency bands) with device-less factory calls like the
+    # reference does; on the GPU they follow torch's default-device context, as under the reference's own `.to(device)` flow
+    ctx = (lambda: torch.device(device)) if device != "cpu" else contextlib.nullcontext
     for i in range(warmup + steps):
         if device != "cpu":
             torch.cuda.synchronize()
         t0 = time.perf_counter()
-        out = O.run_one_iter_of_nerf(CFG["H"], CFG["W"], CFG["focal"], sd_c, sd_f, ro, rd, options,
-                                     enc_xyz=(CFG["L_xyz"], True, True), enc_dir=(4, True, True))
+        with ctx():
+            out = O.run_one_iter_of_nerf(CFG["H"], CFG["W"], CFG["focal"], sd_c, sd_f, ro, rd, options,
+                                         enc_xyz=(CFG["L_xyz"], True, True), enc_dir=(4, True, True))
         loss = O.nerf_loss(out, tgt)
         opt.zero_grad()
         loss.backward()

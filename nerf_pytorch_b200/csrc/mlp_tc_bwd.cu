@@ -45,9 +45,9 @@ constexpr int kDrainWarp0 = 12, kDrainThreads = 128;
 constexpr int kEpi = 256;
 constexpr int kWStage = 96 * 128;                 // one k-step of a 128-wide layer: 3 copies x 2 slabs x 128 x 16 B
 constexpr int kMaxWStages = 6;
-constexpr int kGBytes = 98304;                    // G tile: two hi blocks (alternating layers) + one lo block, 32 KB each
+constexpr int kGBytes = 65536;                    // G tile: hi block 32 KB, lo block 32 KB (128 features)
 constexpr int kXBytes = 65536;                    // activation tile of the running job
-constexpr int kStgBytes = 8192;                   // staging chunk: 128 rows x 16 fp32; two alternate
+constexpr int kStgBytes = 8192;                   // staging chunk: 128 rows x 16 fp32; two per column half (double buffer)
 constexpr int kIndBytes = 4096;                   // ray-indicator tile: 128 points x 16 "features" (hi only)
 constexpr int kMaxRays = 10;
 constexpr uint32_t kTmemColsB = 512;
@@ -55,17 +55,19 @@ constexpr uint32_t kColAcc = 0, kColMain = 128, kMainStride = 144, kIndOff = 128
 constexpr int kSmemLimitB = 232448 - 1024;
 
 struct SmemMapB {
-  int g, x, stg, ind, headw, bgrad, encd, misc, bars, ring, total, n_stages;
+  int g, x, stg, ind, dtile, headw, bgrad, dgrad, encd, misc, bars, ring, total, n_stages;
 };
 __host__ __device__ inline SmemMapB smem_map_b(const Plan& p) {
   SmemMapB m;
   int off = 0;
   m.g = off;      off += kGBytes;
   m.x = off;      off += kXBytes;
-  m.stg = off;    off += 2 * kStgBytes;
+  m.stg = off;    off += 4 * kStgBytes;
   m.ind = off;    off += kIndBytes;
+  m.dtile = off;  off += 2 * kIndBytes;           // d_raw as a 16-column operand tile (hi block, lo block)
   m.headw = off;  off += (4 * 128 + 3 * 64 + 16) * 4;
   m.bgrad = off;  off += (p.enc_cum[0] + 8) * 4;   // bias gradients of every gemm layer + the heads' (8)
+  m.dgrad = off;  off += 64 * 28 * 4;              // direction-encoding part of dW(layers_dir[0]): [n][e], e < 28
   m.encd = off;   off += kMaxRays * 32 * 4;
   m.misc = off;   off += 64;
   m.bars = off;   off += 256;
@@ -170,8 +172,10 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
   uint8_t* sG = sm + mp.g;
   uint8_t* sX = sm + mp.x;
   uint8_t* sInd = sm + mp.ind;
+  uint8_t* sD = sm + mp.dtile;
   float* s_headw = reinterpret_cast<float*>(sm + mp.headw);
   float* s_bgrad = reinterpret_cast<float*>(sm + mp.bgrad);
+  float* s_dgrad = reinterpret_cast<float*>(sm + mp.dgrad);
   float* s_encd = reinterpret_cast<float*>(sm + mp.encd);
   uint32_t* s_max = reinterpret_cast<uint32_t*>(sm + mp.misc);      // [2]: tile max of |d_raw| (alternating tiles)
   float* s_us = reinterpret_cast<float*>(sm + mp.misc) + 2;         // [2]: the tile's unscale factor, for the drain
@@ -186,8 +190,7 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
   uint64_t* xl_free = xh_free + 1;
   uint64_t* job_done = xl_free + 1;             // [2][kMaxJobs]: job i of a layer of that parity complete
   uint64_t* acc_free = job_done + 2 * kMaxJobs; // [2]: the drain is done with the accumulators of that parity
-  uint64_t* glo_free = acc_free + 2;            // the layer's last MMA reading the G tile's lo block has completed
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(glo_free + 1);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(acc_free + 2);
   const uint32_t n_stages = (uint32_t)mp.n_stages;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -210,7 +213,6 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
     for (int i = 0; i < 2 * kMaxJobs; ++i) mbar_init(&job_done[i], 1);
     mbar_init(&acc_free[0], kDrainThreads);
     mbar_init(&acc_free[1], kDrainThreads);
-    mbar_init(glo_free, 1);
     fence_barrier_init();
     s_max[0] = s_max[1] = 0u;
   }
@@ -222,8 +224,10 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
   for (int i = tid; i < hw1; i += kThreadsB) s_headw[i] = blob[p.h[0].w_off + i];
   for (int i = tid; i < hw2; i += kThreadsB) s_headw[hw1 + i] = blob[p.h[1].w_off + i];
   for (int i = tid; i < p.enc_cum[0] + 8; i += kThreadsB) s_bgrad[i] = 0.f;
+  for (int i = tid; i < 64 * 28; i += kThreadsB) s_dgrad[i] = 0.f;
   for (int i = tid; i < kMaxRays * 32; i += kThreadsB) s_encd[i] = 0.f;
   for (int i = tid; i < kGBytes / 16; i += kThreadsB) reinterpret_cast<uint4*>(sG)[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = tid; i < 2 * kIndBytes / 16; i += kThreadsB) reinterpret_cast<uint4*>(sD)[i] = make_uint4(0u, 0u, 0u, 0u);
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
@@ -255,7 +259,7 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
         }
     }
   } else if (warp == 10) {
-    // ===================== activation-tile producer: hi block, then lo block of every job, in job order ============
+    // ===================== activation-tile producer: lo block, then hi block of every job, in job order ============
     if (lane == 0) {
       uint32_t ph = 0;  // phase of the free barriers this job waits on (flips once per job)
       for (int it = 0; it < my_tiles; ++it) {
@@ -269,12 +273,12 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
                                      stash + (size_t)P_pad * (jq.src_enc ? p.enc_cum[0] : p.g[jq.src].cum_n)) +
                                  (size_t)tile * tile_bytes(w);
             const uint32_t hb = (uint32_t)tile_half_bytes(w);
-            PROF_SCOPE(17, mbar_wait(xh_free, ph ^ 1));
-            mbar_arrive_expect_tx(xh_full, hb);
-            bulk_g2s(sX, src, hb, xh_full);
             PROF_SCOPE(16, mbar_wait(xl_free, ph ^ 1));
             mbar_arrive_expect_tx(xl_full, hb);
             bulk_g2s(sX + 32768, src + hb, hb, xl_full);
+            PROF_SCOPE(17, mbar_wait(xh_free, ph ^ 1));
+            mbar_arrive_expect_tx(xh_full, hb);
+            bulk_g2s(sX, src, hb, xh_full);
             ph ^= 1;
           }
         }
@@ -287,19 +291,14 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
     uint32_t free_ph[2] = {0u, 0u};
     const uint32_t t_acc = tmem + kColAcc;
     // every descriptor is built ONCE; the loops only advance start-address fields (tc_common.cuh desc_adv)
-    // G tile: hi block of layer parity 0 at +0, of parity 1 at +32 KB, lo block (every layer) at +64 KB
-    const uint64_t g_hi_k0 = make_desc(smem_u32(sG), 128, 2048), g_lo_k = desc_adv(g_hi_k0, 65536);  // K-major view (chain A)
-    const uint64_t g_hi_m0 = make_desc(smem_u32(sG), 2048, 128), g_lo_m = desc_adv(g_hi_m0, 65536);  // MN-major view (job A)
+    const uint64_t g_hi_k = make_desc(smem_u32(sG), 128, 2048), g_lo_k = desc_adv(g_hi_k, 32768);    // K-major view (chain A)
+    const uint64_t g_hi_m = make_desc(smem_u32(sG), 2048, 128), g_lo_m = desc_adv(g_hi_m, 32768);    // MN-major view (job A)
     const uint64_t ind_d = make_desc(smem_u32(sInd), 256, 128);
-    // d_raw as a 16-column operand (heads' jobs, first layer of a tile): feature rows 64..79 of that layer's G tile
-    // (rows 64..67 carry d_raw, the rest is zero): MN-major view, 8-point blocks 2048 B apart
-    const uint64_t d_hi_d0 = make_desc(smem_u32(sG) + 1024, 2048, 128), d_lo_d = desc_adv(d_hi_d0, 65536);
+    const uint64_t d_hi_d = make_desc(smem_u32(sD), 256, 128), d_lo_d = desc_adv(d_hi_d, kIndBytes);
     const uint32_t x_hi_a = smem_u32(sX), x_lo_a = x_hi_a + 32768;
     for (int it = 0; it < my_tiles; ++it)
       for (int e = 0; e < E; ++e, ++gev) {
         const GemmLayer& g = p.g[E - 1 - e];
-        const uint64_t g_hi_k = desc_adv(g_hi_k0, (gev & 1u) * 32768u), g_hi_m = desc_adv(g_hi_m0, (gev & 1u) * 32768u);
-        const uint64_t d_hi_d = desc_adv(d_hi_d0, (gev & 1u) * 32768u);
         PROF_SCOPE(10, mbar_wait(bar_g, g_ph));
         g_ph ^= 1;
         tc_fence_after();
@@ -334,12 +333,7 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
           free_ph[gev & 1u] ^= 1;
           tc_fence_after();
         }
-        // Pass order of a job: (1) G_lo x X_hi, (2) G_hi x X_lo, (3) G_hi x X_hi with the 2^-11 fold on its first
-        // MMA.  The lo block of the G tile is read by pass 1 only: after the layer's last pass 1 it is released
-        // (glo_free) and the epilogue may write the NEXT layer's gradients while passes 2 and 3 still run -- its hi
-        // block goes to the other hi buffer.
         const int nj = bp.n_jobs[e];
-        const int last_g = nj - 1;  // last job reading the lo block (the heads' jobs read d_raw from it)
         for (int i = 0; i < nj; ++i) {
           const BwdJob& jq = bp.jobs[e][i];
           const int w = jq.n_b;
@@ -349,27 +343,26 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
           if (jq.kind == 1) {
             // head job: A = activation tile (rows = its features: SBO 128, K = points: LBO fstr), B = d_raw tile (N = 16)
             const uint32_t id16 = make_idesc_f16_mn(16, 1, 1);
-            PROF_SCOPE(12, mbar_wait(xh_full, x_ph));
+            PROF_SCOPE(11, mbar_wait(xl_full, x_ph));
             tc_fence_after();
             if (elect_one()) {
 #pragma unroll
               for (int ks = 0; ks < 8; ++ks)
-                mma_ss_f16(d, desc_adv(x_hi_d, ks * 2 * fstr), desc_adv(d_lo_d, ks * 4096), id16, ks > 0 ? 1u : 0u);
-              if (i == last_g) mma_commit(glo_free);
+                mma_ss_f16(d, desc_adv(x_lo_d, ks * 2 * fstr), desc_adv(d_hi_d, ks * 512), id16, ks > 0 ? 1u : 0u);
+              mma_commit(xl_free);
             }
             __syncwarp();
-            PROF_SCOPE(11, mbar_wait(xl_full, x_ph));
+            PROF_SCOPE(12, mbar_wait(xh_full, x_ph));
             tc_fence_after();
             x_ph ^= 1;
             if (elect_one()) {
 #pragma unroll
               for (int ks = 0; ks < 8; ++ks)
-                mma_ss_f16(d, desc_adv(x_lo_d, ks * 2 * fstr), desc_adv(d_hi_d, ks * 4096), id16, 1u);
-              mma_commit(xl_free);
+                mma_ss_f16(d, desc_adv(x_hi_d, ks * 2 * fstr), desc_adv(d_lo_d, ks * 512), id16, 1u);
               mma_ss_f16_scale11(d, x_hi_d, d_hi_d, id16);
 #pragma unroll
               for (int ks = 1; ks < 8; ++ks)
-                mma_ss_f16(d, desc_adv(x_hi_d, ks * 2 * fstr), desc_adv(d_hi_d, ks * 4096), id16, 1u);
+                mma_ss_f16(d, desc_adv(x_hi_d, ks * 2 * fstr), desc_adv(d_hi_d, ks * 512), id16, 1u);
               mma_commit(xh_free);
               mma_commit(&job_done[(gev & 1u) * kMaxJobs + i]);
             }
@@ -377,38 +370,35 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
             continue;
           }
           const uint32_t id_mn = make_idesc_f16_mn(w, 1, 1);
-          const uint32_t id16 = make_idesc_f16_mn(16, 1, 1);
-          const uint32_t di = d + kIndOff;
           // A = G^T: rows = features (SBO 128), K = points (LBO 16 * 128); one k-step = 16 points = 2 point blocks
-          PROF_SCOPE(12, mbar_wait(xh_full, x_ph));
+          PROF_SCOPE(11, mbar_wait(xl_full, x_ph));
           tc_fence_after();
           if (elect_one()) {
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks)
-              mma_ss_f16(d, desc_adv(g_lo_m, ks * 4096), desc_adv(x_hi_d, ks * 2 * fstr), id_mn, ks > 0 ? 1u : 0u);
-            if (i == 0) {
-              // indicator job: sums[n][j] = sum over the points of ray j of the tile of G[p][n] (16 columns)
-#pragma unroll
-              for (int ks = 0; ks < 8; ++ks)
-                mma_ss_f16(di, desc_adv(g_lo_m, ks * 4096), desc_adv(ind_d, ks * 512), id16, ks > 0 ? 1u : 0u);
-            }
-            if (i == last_g) mma_commit(glo_free);
+              mma_ss_f16(d, desc_adv(g_hi_m, ks * 4096), desc_adv(x_lo_d, ks * 2 * fstr), id_mn, ks > 0 ? 1u : 0u);
+            mma_commit(xl_free);
           }
           __syncwarp();
-          PROF_SCOPE(11, mbar_wait(xl_full, x_ph));
+          PROF_SCOPE(12, mbar_wait(xh_full, x_ph));
           tc_fence_after();
           x_ph ^= 1;
           if (elect_one()) {
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks)
-              mma_ss_f16(d, desc_adv(g_hi_m, ks * 4096), desc_adv(x_lo_d, ks * 2 * fstr), id_mn, 1u);
-            mma_commit(xl_free);
+              mma_ss_f16(d, desc_adv(g_lo_m, ks * 4096), desc_adv(x_hi_d, ks * 2 * fstr), id_mn, 1u);
             mma_ss_f16_scale11(d, g_hi_m, x_hi_d, id_mn);
 #pragma unroll
             for (int ks = 1; ks < 8; ++ks)
               mma_ss_f16(d, desc_adv(g_hi_m, ks * 4096), desc_adv(x_hi_d, ks * 2 * fstr), id_mn, 1u);
             mma_commit(xh_free);
             if (i == 0) {
+              // indicator job: sums[n][j] = sum over the points of ray j of the tile of G[p][n] (16 columns)
+              const uint32_t id16 = make_idesc_f16_mn(16, 1, 1);
+              const uint32_t di = d + kIndOff;
+#pragma unroll
+              for (int ks = 0; ks < 8; ++ks)
+                mma_ss_f16(di, desc_adv(g_lo_m, ks * 4096), desc_adv(ind_d, ks * 512), id16, ks > 0 ? 1u : 0u);
               mma_ss_f16_scale11(di, g_hi_m, ind_d, id16);
 #pragma unroll
               for (int ks = 1; ks < 8; ++ks)
@@ -426,10 +416,7 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
     const int row = tid - kDrainWarp0 * 32;
     const uint32_t lane_base = ((uint32_t)((warp & 3) * 32)) << 16;
     float* stg = reinterpret_cast<float*>(sm + mp.stg);
-    float dacc[28];  // direction-encoding part of dW(layers_dir[0]) for output feature `row` (< 64), whole kernel
-#pragma unroll
-    for (int k = 0; k < 28; ++k) dacc[k] = 0.f;
-    uint32_t stg_n = 0, gev = 0;  // chunks staged so far (selects one of the two staging buffers); layers drained
+    uint32_t stg_n = 0, gev = 0;  // chunks staged so far (selects one of the four staging buffers); layers drained
     uint32_t job_ph[2][kMaxJobs] = {{0u, 0u, 0u}, {0u, 0u, 0u}};
     for (int it = 0; it < my_tiles; ++it) {
       const int64_t tile = blockIdx.x + (int64_t)it * gridDim.x;
@@ -458,15 +445,14 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
                 atomicAdd(flat_grad + h.flat_w + (size_t)c * h.k + row, __uint_as_float(v16[(h.out_col + c) & 15]) * us);
             continue;
           }
-          // 16-column chunks through two alternating staging buffers: a buffer is rewritten only after the bulk
-          // reduction issued two chunks ago has finished reading it.  (Tried and rejected: red.global.add.v4.f32 straight
-          // from the registers -- 1.3 cycles per lane on the SM side and every CTA hits the same L2 lines: 2.37 -> 2.76 ms.)
+          // 16-column chunks through four rotating staging buffers: a buffer is rewritten only after the bulk
+          // reduction issued four chunks ago has finished reading it
           const int nchunk = j.n_b >> 4;
           for (int c = 0; c < nchunk; ++c) {
             uint32_t v[16];
             tmem_ld16(tmem + lane_base + jcol + 16 * c, v);
-            float* sb = stg + (stg_n & 1u) * (kStgBytes / 4);
-            if (row == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            float* sb = stg + (stg_n & 3u) * (kStgBytes / 4);
+            if (row == 0) asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory");
             bar_half(0);
             tmem_wait_ld();
 #pragma unroll
@@ -492,16 +478,14 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
             if (row < g.n) s_bgrad[g.cum_n + row] += tot * su;
             if (de == 0 && p.use_viewdirs) {
               if (row >= 64 && row < 68) s_bgrad[p.enc_cum[0] + row - 64] += tot * su;  // d_rgb, d_sigma sums
-#pragma unroll
-              for (int k = 0; k < 28; ++k) {
-                if (k < p.dim_dir) {
+              if (row < g.n)
+                for (int k = 0; k < p.dim_dir; ++k) {
                   float a = 0.f;
 #pragma unroll
                   for (int q = 0; q < kMaxRays; ++q)
                     if (q < n_rays_tile) a = fmaf(__uint_as_float(v16[q]), s_encd[q * 32 + k], a);
-                  dacc[k] = fmaf(a, su, dacc[k]);
+                  s_dgrad[row * 28 + k] += a * su;
                 }
-              }
             }
           }
         }
@@ -517,10 +501,9 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
     if (p.use_viewdirs) {
       const GemmLayer& gd = p.g[p.n_gemm - 1];
       const int in_real = gd.k_h + gd.enc_real;
-      if (row < gd.n) {
-#pragma unroll
-        for (int k = 0; k < 28; ++k)
-          if (k < p.dim_dir) atomicAdd(flat_grad + gd.flat_w + (size_t)row * in_real + gd.k_h + k, dacc[k]);
+      for (int i = row; i < gd.n * p.dim_dir; i += kDrainThreads) {
+        const int n = i / p.dim_dir, k = i - n * p.dim_dir;
+        atomicAdd(flat_grad + gd.flat_w + (size_t)n * in_real + gd.k_h + k, s_dgrad[n * 28 + k]);
       }
       if (row < 3) atomicAdd(flat_grad + p.h[1].flat_b + row, s_bgrad[p.enc_cum[0] + row]);
       if (row == 3) atomicAdd(flat_grad + p.h[0].flat_b, s_bgrad[p.enc_cum[0] + 3]);
@@ -533,12 +516,7 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
     const uint32_t t_acc = tmem + lane_base + kColAcc;
     uint32_t acc_ph = 0, gev = 0;  // gev: layers processed so far (parity of the job barriers)
     uint32_t job_ph[2][kMaxJobs] = {{0u, 0u, 0u}, {0u, 0u, 0u}};
-    // Hand-over of the G tile (see the MMA warp): the hi block of layer gev goes to buffer gev & 1, whose last readers
-    // were the jobs of layer gev - 2; the lo block is shared and is released by glo_free of layer gev - 1.  A new tile
-    // also rewrites the indicator / d_raw tiles, which the jobs of layer gev - 1 may still read: there, wait for them too.
-    uint32_t waited = 0;   // layers [0, waited) have had all their jobs waited for
-    int wait_e = 0;        // event index (within its tile) of layer `waited`
-    uint32_t glo_ph = 0;
+    int prev_e = -1;  // the previous layer: its jobs must have finished reading the G tile before this layer's is written
 
     auto wait_jobs = [&](const int de, const uint32_t parity) {  // every job of that layer complete
       const int nj = bp.n_jobs[de];
@@ -651,21 +629,7 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
         if (tid == 0 && blockIdx.x == 0) g_prof[1] += (unsigned long long)(_tb - _ta);
 #endif
         // the previous layer's jobs read the G tile: they must be complete before it is overwritten
-        {
-          const uint32_t need = (e == 0) ? gev : (gev >= 1u ? gev - 1u : 0u);  // layers [0, need) must be complete
-          while (waited < need) {
-            wait_jobs(wait_e, waited & 1u);
-            ++waited;
-            if (++wait_e == E) wait_e = 0;
-          }
-          if (gev >= 1u) {
-            PROF_SCOPE(3, mbar_wait(glo_free, glo_ph));
-            glo_ph ^= 1;
-            tc_fence_after();
-          }
-        }
-        uint8_t* const sGh = sG + (gev & 1u) * 32768u;  // this layer's hi block
-        uint8_t* const sGl = sG + 65536;                // the shared lo block
+        if (prev_e >= 0) wait_jobs(prev_e, (gev - 1u) & 1u);
 #ifdef NERFB200_PROF
         const long long _tc = clock64();
 #endif
@@ -678,8 +642,8 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const int off = tile_piece(row, fb0 + q, 128);
-              *reinterpret_cast<uint4*>(sGh + off) = make_uint4(hi[ch][4 * q], hi[ch][4 * q + 1], hi[ch][4 * q + 2], hi[ch][4 * q + 3]);
-              *reinterpret_cast<uint4*>(sGl + off) =
+              *reinterpret_cast<uint4*>(sG + off) = make_uint4(hi[ch][4 * q], hi[ch][4 * q + 1], hi[ch][4 * q + 2], hi[ch][4 * q + 3]);
+              *reinterpret_cast<uint4*>(sG + 32768 + off) =
                   make_uint4(lo[ch][4 * q], lo[ch][4 * q + 1], lo[ch][4 * q + 2], lo[ch][4 * q + 3]);
             }
           }
@@ -693,18 +657,18 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
             split_f16x2(dr[0], dr[1], h01, l01);
             split_f16x2(dr[2], dr[3], h23, l23);
             const int off = tile_piece(row, 8, 128);
-            *reinterpret_cast<uint4*>(sGh + off) = make_uint4(h01, h23, 0u, 0u);
-            *reinterpret_cast<uint4*>(sGl + off) = make_uint4(l01, l23, 0u, 0u);
+            *reinterpret_cast<uint4*>(sG + off) = make_uint4(h01, h23, 0u, 0u);
+            *reinterpret_cast<uint4*>(sG + 32768 + off) = make_uint4(l01, l23, 0u, 0u);
 #pragma unroll
             for (int q = 9; q < 12; ++q) {
-              *reinterpret_cast<uint4*>(sGh + tile_piece(row, q, 128)) = z4;
-              *reinterpret_cast<uint4*>(sGl + tile_piece(row, q, 128)) = z4;
+              *reinterpret_cast<uint4*>(sG + tile_piece(row, q, 128)) = z4;
+              *reinterpret_cast<uint4*>(sG + 32768 + tile_piece(row, q, 128)) = z4;
             }
           } else {
 #pragma unroll
             for (int q = 12; q < 16; ++q) {
-              *reinterpret_cast<uint4*>(sGh + tile_piece(row, q, 128)) = z4;
-              *reinterpret_cast<uint4*>(sGl + tile_piece(row, q, 128)) = z4;
+              *reinterpret_cast<uint4*>(sG + tile_piece(row, q, 128)) = z4;
+              *reinterpret_cast<uint4*>(sG + 32768 + tile_piece(row, q, 128)) = z4;
             }
           }
         }
@@ -721,6 +685,12 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
             *reinterpret_cast<uint4*>(sInd + tile_piece(row, 0, 16)) = make_uint4(w[0], w[1], w[2], w[3]);
             *reinterpret_cast<uint4*>(sInd + tile_piece(row, 1, 16)) = make_uint4(w[4], w[5], w[6], w[7]);
           } else {
+            // d_raw of this point as a 16-column operand tile (columns 0..3 live): B operand of the heads' jobs
+            uint32_t h01, l01, h23, l23;
+            split_f16x2(dr[0], dr[1], h01, l01);
+            split_f16x2(dr[2], dr[3], h23, l23);
+            *reinterpret_cast<uint4*>(sD + tile_piece(row, 0, 16)) = make_uint4(h01, h23, 0u, 0u);
+            *reinterpret_cast<uint4*>(sD + kIndBytes + tile_piece(row, 0, 16)) = make_uint4(l01, l23, 0u, 0u);
             if (p.use_viewdirs && row < n_rays_tile * 3) {
               const int jr = row / 3, c = row - 3 * jr;
               const float vv = rays[(first_ray + jr) * ray_stride + 8 + c];
@@ -734,6 +704,7 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
         const long long _td2 = clock64();
         if (tid == 0 && blockIdx.x == 0) { g_prof[5] += (unsigned long long)(_td2 - _tc); g_prof[7] += 1; }
 #endif
+        prev_e = e;
         ++gev;
       }
     }
@@ -795,10 +766,6 @@ int bwd_tc_supported(const Plan& p, int n_samples, const char* what) {
   if (rc) return rc;
   if (!p.use_viewdirs) {
     set_error("%s impl=1 (tcgen05): the fused backward needs a view-dependent model (fc_rgb / fc_alpha heads); use impl=0", what);
-    return NERFB200_ERR_UNSUPPORTED;
-  }
-  if (p.dim_dir > 28) {
-    set_error("%s impl=1 (tcgen05): direction encodings wider than 28 not supported by the fused backward; use impl=0", what);
     return NERFB200_ERR_UNSUPPORTED;
   }
   if (smem_map_b(p).n_stages < 2) {

@@ -7,10 +7,6 @@
 #include "tc_common.cuh"
 using namespace nerfb200::tc;
 
-__device__ __forceinline__ uint64_t desc_adv(uint64_t d, uint32_t bytes) {  // advance the 14-bit start-address field
-  return ((d >> 32) << 32) | (uint32_t)((uint32_t)d + (bytes >> 4));
-}
-
 // kMode 0: SS K-major x K-major   1: SS MN x MN   2: TS x K-major   3: pairs (N=128 into D0, N=16 into D1), MN x MN
 template <int kMode, int kN>
 __global__ void __launch_bounds__(128, 1) rate_kernel(long long* out, int reps) {

@@ -51,7 +51,7 @@ __host__ __device__ inline SmemMap smem_map(const Plan& p) {
   SmemMap m;
   m.enc = 0;                                        // 2 slots x 32 KB: encodings as fp16 operand tiles (hi | lo)
   int off = m.enc + 2 * kEncBytes;
-  m.bias = off;      off += p.enc_cum[0] * 4;       // sum of n over the gemm layers (bias / 16)
+  m.bias = off;      off += p.enc_cum[0] * 4;       // sum of n over the gemm layers (bias * 2048 / 16)
   m.headw = off;     off += (4 * 128 + 3 * 64 + 16) * 4;
   m.viewb = off;     off += 2 * kMaxRaysPerTile * 64 * 4;
   m.encd = off;      off += 2 * kMaxRaysPerTile * 32 * 4;
@@ -128,11 +128,11 @@ using namespace tc;
 // One 32-column chunk of one row in the epilogue (the hot loop; ONE instance per kernel: the code must stay inside the
 // instruction cache -- the four head-count specialisations of the previous version, each inlined at two call sites of
 // two slot copies, made the kernel 160 KB and 10 % of the issue slots were instruction-fetch stalls):
-//   ys = max(acc * 2^-11 + bias/16, lb) = activation / 16      (lb = 0 with ReLU, -inf without; the bias already
+//   Y = max(acc + 2048 bias/16, lb), ys = Y / 2048 = activation / 16   (lb = 0 with ReLU, -inf without; the bias already
 //   holds the per-ray direction term for layers_dir[0]); head rows accumulate ys * (16 w) in a separate short pass;
 // then -> fp16 hi / lo -> tensor memory (next layer's A operand) and, in training, the stash tile.
 struct ChunkArgs {
-  const float* bias;      // this layer's bias / 16 (or the per-ray bias of layers_dir[0])
+  const float* bias;      // this layer's bias * 2048 / 16 (or the per-ray bias of layers_dir[0])
   float lb;               // ReLU lower bound
   const float* hw;        // head weights [hn][hk] in smem (pre-multiplied by 16)
   int hk, hn;
@@ -145,16 +145,20 @@ struct ChunkArgs {
 
 template <bool kTrain>
 __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int c0, const ChunkArgs& a, float (&hacc)[4]) {
-  float x[32];
+  // Y = max(acc + 2048 bias/16, lb) = 2048 ys (the accumulator's own scale: the biases are stored pre-multiplied),
+  // x = ys = Y / 2048 exactly
+  float Y[32], x[32];
 #pragma unroll
   for (int j = 0; j < 32; j += 4) {
     const float4 b = *reinterpret_cast<const float4*>(a.bias + c0 + j);
     // NaN-propagating ReLU: an activation or weight beyond the fp16 x 2 range must surface as a non-finite output,
     // never as a silently wrong finite one
-    x[j] = fmax_nan(fmaf(__uint_as_float(v[j]), kLoInv, b.x), a.lb);
-    x[j + 1] = fmax_nan(fmaf(__uint_as_float(v[j + 1]), kLoInv, b.y), a.lb);
-    x[j + 2] = fmax_nan(fmaf(__uint_as_float(v[j + 2]), kLoInv, b.z), a.lb);
-    x[j + 3] = fmax_nan(fmaf(__uint_as_float(v[j + 3]), kLoInv, b.w), a.lb);
+    Y[j] = fmax_nan(__uint_as_float(v[j]) + b.x, a.lb);
+    Y[j + 1] = fmax_nan(__uint_as_float(v[j + 1]) + b.y, a.lb);
+    Y[j + 2] = fmax_nan(__uint_as_float(v[j + 2]) + b.z, a.lb);
+    Y[j + 3] = fmax_nan(__uint_as_float(v[j + 3]) + b.w, a.lb);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) x[j + q] = Y[j + q] * kLoInv;
   }
   if (a.hn > 0) {  // narrow heads reading this layer (2 of the 9 layers): register dot products
 #pragma unroll
@@ -181,7 +185,7 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int c0, 
     // fp16 x 2: two K-adjacent values per tensor-memory column / per 32-bit word of a stash piece
     uint32_t hi[16], lo[16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) split_f16x2(x[2 * j], x[2 * j + 1], hi[j], lo[j]);
+    for (int j = 0; j < 16; ++j) split_f16x2_y(Y[2 * j], Y[2 * j + 1], x[2 * j], x[2 * j + 1], hi[j], lo[j]);
     if (a.has_next) {
       tmem_st16(a.tmem_hi, hi);
       tmem_st16(a.tmem_lo, lo);
@@ -251,7 +255,7 @@ mlp_fwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
   }
   // biases (/16) + head weights (x16, they multiply activation / 16): once per CTA
   for (int gi = 0; gi < p.n_gemm; ++gi)
-    for (int i = tid; i < p.g[gi].n; i += kThreadsTc) s_bias[p.g[gi].cum_n + i] = blob[p.g[gi].b_off + i] * kActScale;
+    for (int i = tid; i < p.g[gi].n; i += kThreadsTc) s_bias[p.g[gi].cum_n + i] = blob[p.g[gi].b_off + i] * (kActScale * kLoScale);
   const int hw1 = p.h[0].n_out * p.h[0].k;
   const int hw2 = p.n_head > 1 ? p.h[1].n_out * p.h[1].k : 0;
   for (int i = tid; i < hw1; i += kThreadsTc) s_headw[i] = blob[p.h[0].w_off + i] * kActInv;
@@ -434,7 +438,7 @@ mlp_fwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
             const int jr = i / gd.n, n = i - jr * gd.n;
             float a = 0.f;
             for (int k = 0; k < p.dim_dir; ++k) a = fmaf(encd[jr * 32 + k], wv[k * gd.n + n], a);
-            viewb[jr * 64 + n] = fmaf(a, kActScale, s_bias[gd.cum_n + n]);  // per-ray bias of layers_dir[0] (/16)
+            viewb[jr * 64 + n] = fmaf(a, kActScale * kLoScale, s_bias[gd.cum_n + n]);  // per-ray bias of layers_dir[0] (x 2048 / 16)
           }
         }
         tc_fence_before();

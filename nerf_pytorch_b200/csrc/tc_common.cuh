@@ -155,6 +155,18 @@ __device__ __forceinline__ void split_f16x2(float x0, float x1, uint32_t& hi, ui
   asm("{\n.reg .b16 a, b;\nmov.b32 {a, b}, %2;\ncvt.f32.f16 %0, a;\ncvt.f32.f16 %1, b;\n}\n" : "=f"(h0), "=f"(h1) : "r"(hi));
   asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"((x1 - h1) * kLoScale), "f"((x0 - h0) * kLoScale));
 }
+// The same split from Y = 2048 x (exact scaling): hi = fp16(x), lo = fp16(Y - 2048 hi) with the mixed-precision FMA
+// (fma.rn.f32.f16: fp16 x fp16 + fp32, one instruction per element, takes the packed halves directly) instead of
+// unpack + subtract + multiply.  Bit-identical to split_f16x2(Y0 / 2048, Y1 / 2048): x - hi is exact in fp32.
+__device__ __forceinline__ void split_f16x2_y(float Y0, float Y1, float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
+  float r0, r1;
+  asm("{\n.reg .b16 a, b, m;\nmov.b32 {a, b}, %2;\nmov.b16 m, 0xE800;\n"   // 0xE800 = -2048 in fp16
+      "fma.rn.f32.f16 %0, a, m, %3;\nfma.rn.f32.f16 %1, b, m, %4;\n}\n"
+      : "=f"(r0), "=f"(r1)
+      : "r"(hi), "f"(Y0), "f"(Y1));
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(r1), "f"(r0));
+}
 // the three weight copies of one pair (same packing)
 __device__ __forceinline__ void split_w3(float w0, float w1, uint32_t& hs, uint32_t& h, uint32_t& l) {
   asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(w1), "f"(w0));

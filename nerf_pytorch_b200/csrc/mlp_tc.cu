@@ -32,8 +32,13 @@
 namespace nerfb200 {
 
 namespace tc {
-constexpr int kEpiThreads = 256;
-constexpr int kThreadsTc = 320;
+constexpr int kEpiThreads = 256;                     // per slot: two dedicated warpgroups
+constexpr int kThreadsTc = 576;                      // 16 epilogue warps + MMA issuer + weight producer: 65536 / 576 -> 112
+                                                     // registers per thread for everyone (no setmaxnreg: a CTA's register
+                                                     // pool is threads x launch registers, NOT the whole file -- a first
+                                                     // version with 640 threads x 96 could not raise 512 threads to 112 and
+                                                     // hung in setmaxnreg.inc)
+constexpr int kMmaWarp = 16, kProdWarp = 17;
 constexpr int kStepsPerStage = 2;                    // k-steps per ring stage
 constexpr int kStageBytes = kStepsPerStage * 96 * 128;  // 24 KB: 3 copies x 2 slabs x 128 rows x 16 B per k-step
 constexpr int kMaxStages = 6;
@@ -222,12 +227,10 @@ mlp_fwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
   // barrier addresses are kept as 32-bit shared-memory addresses (8 bytes per barrier)
   const uint32_t bar_full = smem_u32(bars);                // [kMaxStages]  weights landed
   const uint32_t bar_empty = bar_full + 8 * kMaxStages;    // [kMaxStages]  stage consumed by the MMAs
-  // per slot: A operand columns [0,64) of the next MMA ready AND the accumulator fully drained into registers
-  // (bar_a1), columns [64,128) ready (bar_a2): the MMA's first four k-steps only need the former, so they run
-  // while the epilogue is still working on the second half of its columns.  bar_acc: accumulator complete.
-  const uint32_t bar_a1 = bar_empty + 8 * kMaxStages;      // [2]
-  const uint32_t bar_a2 = bar_a1 + 16;                     // [2]
-  const uint32_t bar_acc = bar_a2 + 16;                    // [2]
+  // per slot: bar_a = the next MMA's A operand is in tensor memory and the accumulator is drained (all 256 threads of
+  // the slot's epilogue group); bar_acc = accumulator complete
+  const uint32_t bar_a = bar_empty + 8 * kMaxStages;       // [2]
+  const uint32_t bar_acc = bar_a + 32;                     // [2]
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 6);
   const uint32_t n_stages = (uint32_t)mp.n_stages;
 
@@ -242,13 +245,12 @@ mlp_fwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
       mbar_init(&bars[kMaxStages + i], 1);
     }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&bars[2 * kMaxStages + s], kEpiThreads);
-      mbar_init(&bars[2 * kMaxStages + 2 + s], kEpiThreads);
-      mbar_init(&bars[2 * kMaxStages + 4 + s], 1);
+      mbar_init(&bars[2 * kMaxStages + s], kEpiThreads);      // bar_a
+      mbar_init(&bars[2 * kMaxStages + 4 + s], 1);            // bar_acc
     }
     fence_barrier_init();
   }
-  if (warp == 8) {
+  if (warp == kMmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)),
                  "r"(kTmemCols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
@@ -275,7 +277,7 @@ mlp_fwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
   const Seq seq(E, my_tiles);
   const uint32_t ring_a = smem_u32(sm + mp.ring);
 
-  if (warp == 9) {
+  if (warp == kProdWarp) {
     // ===================== weight producer =====================
     if ((tid & 31) == 0) {
       Pipe pp;
@@ -297,7 +299,7 @@ mlp_fwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
         swap2(cur, oth);
       }
     }
-  } else if (warp == 8) {
+  } else if (warp == kMmaWarp) {
     // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
     Pipe pp;
     uint32_t a_ph = 0, a_ph_oth = 0;  // phase of this slot's bar_a1 / bar_a2 (swapped with the cursors)
@@ -314,16 +316,9 @@ mlp_fwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
         const uint64_t b_ring = make_desc(ring_a, slab_b, 128);
         const uint64_t e_hi_d0 = make_desc(smem_u32(sm + mp.enc) + s * kEncBytes, 128, (uint32_t)(enc_w >> 3) * 128u);
         const uint64_t e_lo_d0 = desc_adv(e_hi_d0, (uint32_t)enc_half);
-        constexpr int kHalfSteps = 4;  // k-steps covered by A columns [0, 64)
-        mbar_wait(bar_a1 + 8 * s, a_ph);
+        mbar_wait(bar_a + 8 * s, a_ph);
         tc_fence_after();
-        bool second = false;  // bar_a2 of this MMA consumed?
         for (int ks0 = 0; ks0 < mi.ksteps; ks0 += kStepsPerStage) {
-          if (!second && (ks0 + kStepsPerStage > kHalfSteps || mi.ksteps_h == 0)) {
-            mbar_wait(bar_a2 + 8 * s, a_ph);  // this stage touches A columns >= 64 (or the encodings)
-            tc_fence_after();
-            second = true;
-          }
           mbar_wait(bar_full + 8 * pp.stage, pp.phase);
           tc_fence_after();
           const uint64_t b_st = desc_adv(b_ring, pp.stage * (uint32_t)kStageBytes);
@@ -354,7 +349,6 @@ mlp_fwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
           __syncwarp();
           pp.advance(n_stages);
         }
-        if (!second) mbar_wait(bar_a2 + 8 * s, a_ph);  // keep the phases aligned for short layers
         a_ph ^= 1;
         if (elect_one()) mma_commit(bar_acc + 8 * s);  // accumulator of this MMA complete
         __syncwarp();
@@ -364,14 +358,17 @@ mlp_fwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
       swap2(a_ph, a_ph_oth);
     }
   } else {
-    // ===================== prologue / epilogue warps =====================
-    const int row = tid & 127, half = tid >> 7;
+    // ===================== prologue / epilogue warps: warps 0-7 serve slot 0, warps 8-15 slot 1 =====================
+    // Each slot's tile chain runs on its own eight warps, so the two slots' epilogues overlap on the four schedulers
+    // (four epilogue warps each instead of two taking turns) and each slot's MMAs run under the other slot's epilogue.
+    const int s = warp >> 3;               // the slot this warp serves
+    const int gtid = tid & 255;            // thread index inside the slot's group
+    const int row = gtid & 127, half = gtid >> 7;
     const uint32_t lane_base = ((uint32_t)((warp & 3) * 32)) << 16;
-    TileState ts, ts_oth;   // this half-tick's slot and the other one (swapped with the cursors)
-    Cursor cur = seq.c0, oth = seq.c1;
+    TileState ts;
+    auto epi_bar = [&]() { asm volatile("bar.sync %0, 256;" ::"r"(1 + s) : "memory"); };
 
-    // ONE instance of the event code serves both slots (slot = h & 1)
-    auto run_event = [&](const int s, const int j, const int e) {
+    auto run_event = [&](const int j, const int e) {
       const uint32_t t_acc = tmem + lane_base + s * kSlotCols + kColAcc;
       const uint32_t t_ahi = tmem + lane_base + s * kSlotCols + kColAhi;
       const uint32_t t_alo = tmem + lane_base + s * kSlotCols + kColAlo;
@@ -395,8 +392,8 @@ mlp_fwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
         const int n_rays_tile = (int)(last_pt / S - first_ray) + 1;
         ts.ray_slot = (int)(ray - first_ray);
         if (kTrain) {  // the previous tile's encoding store must have finished reading this buffer
-          if (tid == 0) bulk_wait_read();
-          epi_bar256();
+          if (gtid == 0) bulk_wait_read();
+          epi_bar();
         }
         {
           const float* rr = rays + ray * ray_stride;
@@ -426,15 +423,15 @@ mlp_fwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
         }
         // ---- per-ray direction term of layers_dir[0]: vb[ray][n] = (sum_k enc_dir(ray)[k] * W[n][H + k] + b[n]) / 16
         if (p.use_viewdirs) {
-          if (tid < n_rays_tile * 3) {
-            const int jr = tid / 3, c = tid - 3 * jr;
+          if (gtid < n_rays_tile * 3) {
+            const int jr = gtid / 3, c = gtid - 3 * jr;
             const float v = rays[(first_ray + jr) * ray_stride + 8 + c];
             encode_coord(v, c, p.inc_dir, 0, p.n_freq_dir, p.freq_dir, encd + jr * 32);
           }
-          epi_bar256();
+          epi_bar();
           const GemmLayer& gd = p.g[p.n_gemm - 1];
           const float* wv = blob + gd.wt_off + (size_t)gd.k_h * gd.n;  // rows k_h.. of Wt[k][n]
-          for (int i = tid; i < n_rays_tile * gd.n; i += kEpiThreads) {
+          for (int i = gtid; i < n_rays_tile * gd.n; i += kEpiThreads) {
             const int jr = i / gd.n, n = i - jr * gd.n;
             float a = 0.f;
             for (int k = 0; k < p.dim_dir; ++k) a = fmaf(encd[jr * 32 + k], wv[k * gd.n + n], a);
@@ -443,12 +440,11 @@ mlp_fwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
         }
         tc_fence_before();
         fence_proxy_async();  // E was written through the generic proxy; the MMAs / the bulk store read it via the async proxy
-        epi_bar256();         // also publishes viewb
-        if (kTrain && tid == 0)  // the encoding tile goes to the stash as it is: one bulk store
+        epi_bar();         // also publishes viewb
+        if (kTrain && gtid == 0)  // the encoding tile goes to the stash as it is: one bulk store
           bulk_s2g(reinterpret_cast<uint8_t*>(stash + (size_t)P_pad * p.enc_cum[0]) + (size_t)ts.tile * tile_bytes(enc_w),
                    e_hi, (uint32_t)tile_bytes(enc_w));
-        mbar_arrive(bar_a1 + 8 * s);
-        mbar_arrive(bar_a2 + 8 * s);
+        mbar_arrive(bar_a + 8 * s);
         return;
       }
 
@@ -485,43 +481,33 @@ mlp_fwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
         if (kTrain)
           ca.stash_hi = reinterpret_cast<uint8_t*>(stash + (size_t)P_pad * g.cum_n) + (size_t)ts.tile * tile_bytes(g.n) +
                         tile_piece(row, 0, g.n);
-        // column chunks of this thread: first [32*half, +32), second [64 + 32*half, +32) (128-wide layers only).
-        // Both are pulled out of the accumulator up front; after the first chunk's A columns are stored the
-        // next MMA may start its first four k-steps (bar_a1), the second chunk follows under that shadow.
+        // column chunks of this thread: [32*half, +32) and, for 128-wide layers, [64 + 32*half, +32), one after the
+        // other (112 registers per thread: one 32-column chunk at a time)
         const int nch = g.n >> 6;  // 2 for 128-wide layers, 1 for 64-wide ones
-        const int c0a = 32 * half, c0b = 64 + 32 * half;
-        uint32_t v0[32], v1[32];
-        tmem_ld32(t_acc + c0a, v0);
-        if (nch == 2) tmem_ld32(t_acc + c0b, v1);
-        tmem_wait_ld();
-        ca.mword_out = mask_row ? mask_row + (c0a >> 5) : nullptr;
-        ca.tmem_hi = t_ahi + c0a / 2;  // two fp16 per tensor-memory column
-        ca.tmem_lo = t_alo + c0a / 2;
-        epilogue_chunk<kTrain>(v0, c0a, ca, hacc);
-        if (has_next) {
-          tmem_wait_st();
-          tc_fence_before();
-          mbar_arrive(bar_a1 + 8 * s);
-        }
-        if (nch == 2) {
-          ca.mword_out = mask_row ? mask_row + (c0b >> 5) : nullptr;
-          ca.tmem_hi = t_ahi + c0b / 2;
-          ca.tmem_lo = t_alo + c0b / 2;
-          epilogue_chunk<kTrain>(v1, c0b, ca, hacc);
+#pragma unroll 1
+        for (int ch = 0; ch < nch; ++ch) {
+          const int c0 = 64 * ch + 32 * half;
+          uint32_t v[32];
+          tmem_ld32(t_acc + c0, v);
+          tmem_wait_ld();
+          ca.mword_out = mask_row ? mask_row + (c0 >> 5) : nullptr;
+          ca.tmem_hi = t_ahi + c0 / 2;  // two fp16 per tensor-memory column
+          ca.tmem_lo = t_alo + c0 / 2;
+          epilogue_chunk<kTrain>(v, c0, ca, hacc);
         }
       }
 
       if (hsel >= 0 && half == 1)
         *reinterpret_cast<float4*>(hpart + (hsel * 128 + row) * 4) = make_float4(hacc[0], hacc[1], hacc[2], hacc[3]);
-      if (has_next) {
+      if (has_next) {  // A operand of the next layer stored, accumulator drained: the slot's next MMA may start
         tmem_wait_st();
         tc_fence_before();
-        mbar_arrive(bar_a2 + 8 * s);
+        mbar_arrive(bar_a + 8 * s);
       } else {
         tc_fence_before();
       }
       if (hsel >= 0) {
-        epi_bar256();  // head partials in hpart
+        epi_bar();  // head partials in hpart
         if (half == 0 && valid) {
           const float4 o = *reinterpret_cast<const float4*>(hpart + (hsel * 128 + row) * 4);
           const float tot[4] = {hacc[0] + o.x + s_headb[hsel * 4 + 0], hacc[1] + o.y + s_headb[hsel * 4 + 1],
@@ -533,19 +519,17 @@ mlp_fwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
       }
     };
 
+    const int n_mine = s ? seq.c1.n : seq.c0.n;
 #pragma unroll 1
-    for (int h = 0; h < seq.half_ticks; ++h) {
-      if (cur.active()) run_event(h & 1, cur.j, cur.e);
-      cur.next(E);
-      swap2(cur, oth);
-      swap2(ts, ts_oth);
-    }
+    for (int j = 0; j < n_mine; ++j)
+#pragma unroll 1
+      for (int e = 0; e < E; ++e) run_event(j, e);
+    if (gtid == 0) bulk_wait_all();  // this group's encoding-tile stores
   }
 
-  if (tid == 0) bulk_wait_all();
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols));
+  if (warp == kMmaWarp) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols));
 }
 
 int tc_supported(const Plan& p, int n_samples, const char* what) {

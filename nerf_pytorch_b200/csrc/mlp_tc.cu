@@ -50,7 +50,7 @@ constexpr int kSmemLimit = 232448 - 1024;            // 227 KB minus the alignme
 
 // Shared memory map (bytes from the 1 KB-aligned base), computed identically on host and device.
 struct SmemMap {
-  int enc, ring, bias, headw, viewb, encd, hpart, bars, total, n_stages;
+  int enc, ring, bias, headw, viewb, encd, hpart, wv, bars, total, n_stages;
 };
 __host__ __device__ inline SmemMap smem_map(const Plan& p) {
   SmemMap m;
@@ -61,6 +61,7 @@ __host__ __device__ inline SmemMap smem_map(const Plan& p) {
   m.viewb = off;     off += 2 * kMaxRaysPerTile * 64 * 4;
   m.encd = off;      off += 2 * kMaxRaysPerTile * 32 * 4;
   m.hpart = off;     off += 2 * 2 * 128 * 4 * 4;    // [slot][head][row][4]
+  m.wv = off;        off += 32 * 64 * 4;            // direction-encoding rows of layers_dir[0]'s weight: Wt[k_h + k][n]
   m.bars = off;      off += 256;
   off = (off + 1023) & ~1023;
   m.ring = off;
@@ -130,6 +131,30 @@ struct TileState {
 
 using namespace tc;
 
+// Development build only (make EXTRA=-DNERFB200_PROF): lane 0 of warp 0 (slot 0's epilogue), of the MMA warp and of the
+// producer warp of CTA 0 add up the cycles they spend in each phase (shared-memory counters, flushed at the end).
+#ifdef NERFB200_PROF
+__device__ unsigned long long g_prof_fwd[32];
+#define FPROF_ON (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (threadIdx.x < 32 || threadIdx.x >= 512))
+#define FPROF_SCOPE(i, stmt) do { const long long _ps = clock64(); stmt; if (FPROF_ON) s_prof[i] += (uint32_t)(clock64() - _ps); } while (0)
+#define FPROF_MARK(name) const long long name = clock64()
+#define FPROF_SINCE(i, name) do { if (FPROF_ON) s_prof[i] += (uint32_t)(clock64() - name); } while (0)
+#define FPROF_COUNT(i) do { if (FPROF_ON) s_prof[i] += 1u; } while (0)
+extern "C" void nerfb200_prof_read_fwd(unsigned long long* out32, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out32, g_prof_fwd, sizeof(g_prof_fwd));
+  if (reset) {
+    unsigned long long z[32] = {0};
+    cudaMemcpyToSymbol(g_prof_fwd, z, sizeof(z));
+  }
+}
+#else
+#define FPROF_SCOPE(i, stmt) do { stmt; } while (0)
+#define FPROF_MARK(name)
+#define FPROF_SINCE(i, name)
+#define FPROF_COUNT(i)
+#endif
+
 // One 32-column chunk of one row in the epilogue (the hot loop; ONE instance per kernel: the code must stay inside the
 // instruction cache -- the four head-count specialisations of the previous version, each inlined at two call sites of
 // two slot copies, made the kernel 160 KB and 10 % of the issue slots were instruction-fetch stalls):
@@ -181,9 +206,11 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int c0, 
     }
   }
   if (kTrain && a.mword_out) {
+    // ReLU bit mask: Y >= 0 here, so Y > 0 <=> its bit pattern is a positive integer; min(bits, 1) is the mask bit and
+    // bits = 2 bits + m shifts it in (2 instructions per element), element 31 first so that element j ends at bit j
     uint32_t bits = 0;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) bits |= (x[j] > 0.f ? 1u : 0u) << j;
+    for (int j = 31; j >= 0; --j) bits = bits * 2u + min(__float_as_uint(Y[j]), 1u);
     *a.mword_out = bits;
   }
   if (a.has_next || kTrain) {
@@ -223,6 +250,7 @@ mlp_fwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
   float* s_viewb = reinterpret_cast<float*>(sm + mp.viewb);
   float* s_encd = reinterpret_cast<float*>(sm + mp.encd);
   float* s_hpart = reinterpret_cast<float*>(sm + mp.hpart);
+  float* s_wv = reinterpret_cast<float*>(sm + mp.wv);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + mp.bars);
   // barrier addresses are kept as 32-bit shared-memory addresses (8 bytes per barrier)
   const uint32_t bar_full = smem_u32(bars);                // [kMaxStages]  weights landed
@@ -233,6 +261,10 @@ mlp_fwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
   const uint32_t bar_acc = bar_a + 32;                     // [2]
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 6);
   const uint32_t n_stages = (uint32_t)mp.n_stages;
+#ifdef NERFB200_PROF
+  uint32_t* s_prof = reinterpret_cast<uint32_t*>(bars) + 40;  // 24 counters in the spare part of the barrier block
+  if (threadIdx.x < 24) s_prof[threadIdx.x] = 0u;
+#endif
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int64_t P_pad = n_tiles * kTileRows;       // the stash sections are sized in whole tiles
@@ -266,6 +298,13 @@ mlp_fwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
   if (tid < 4) s_headb[tid] = blob[p.h[0].b_off + tid];
   if (tid >= 4 && tid < 8) s_headb[tid] = p.n_head > 1 ? blob[p.h[1].b_off + tid - 4] : 0.f;
   for (int i = tid; i < 2 * kMaxRaysPerTile * 32; i += kThreadsTc) s_encd[i] = 0.f;  // padding channels stay zero
+  if (p.use_viewdirs) {
+    // the per-ray direction term reads these 27 x 64 weights for every tile: from shared memory, not from L2 (the
+    // dependent global loads made the prologue 10.6 k cycles per tile)
+    const GemmLayer& gd = p.g[p.n_gemm - 1];
+    const float* wv_g = blob + gd.wt_off + (size_t)gd.k_h * gd.n;  // rows k_h.. of Wt[k][n]
+    for (int i = tid; i < p.dim_dir * gd.n; i += kThreadsTc) s_wv[i] = wv_g[i];
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -288,7 +327,7 @@ mlp_fwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
           const MmaInfo mi = mma_info(p, blob, cur.e);
           for (int ks = 0; ks < mi.ksteps; ks += kStepsPerStage) {
             const uint32_t bytes = (uint32_t)min(kStepsPerStage, mi.ksteps - ks) * mi.kbytes;
-            mbar_wait(bar_empty + 8 * pp.stage, pp.phase ^ 1);
+            FPROF_SCOPE(11, mbar_wait(bar_empty + 8 * pp.stage, pp.phase ^ 1));
             mbar_arrive_expect_tx(bar_full + 8 * pp.stage, bytes);
             bulk_g2s_hint(ring_a + pp.stage * kStageBytes, mi.src + (size_t)ks * mi.kbytes, bytes,
                           bar_full + 8 * pp.stage, pol);
@@ -316,13 +355,19 @@ mlp_fwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
         const uint64_t b_ring = make_desc(ring_a, slab_b, 128);
         const uint64_t e_hi_d0 = make_desc(smem_u32(sm + mp.enc) + s * kEncBytes, 128, (uint32_t)(enc_w >> 3) * 128u);
         const uint64_t e_lo_d0 = desc_adv(e_hi_d0, (uint32_t)enc_half);
-        mbar_wait(bar_a + 8 * s, a_ph);
+        FPROF_MARK(_tm);
+        FPROF_SCOPE(8, mbar_wait(bar_a + 8 * s, a_ph));
         tc_fence_after();
         for (int ks0 = 0; ks0 < mi.ksteps; ks0 += kStepsPerStage) {
-          mbar_wait(bar_full + 8 * pp.stage, pp.phase);
+          FPROF_SCOPE(9, mbar_wait(bar_full + 8 * pp.stage, pp.phase));
           tc_fence_after();
           const uint64_t b_st = desc_adv(b_ring, pp.stage * (uint32_t)kStageBytes);
+#if defined(NERFB200_EXP) && NERFB200_EXP == 2   // timing experiment: no MMAs (results are garbage)
+          if (elect_one()) mma_commit(bar_empty + 8 * pp.stage);
+          if (false) {
+#else
           if (elect_one()) {
+#endif
 #pragma unroll
             for (int hh = 0; hh < kStepsPerStage; ++hh) {
               const int ks = ks0 + hh;
@@ -352,6 +397,8 @@ mlp_fwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
         a_ph ^= 1;
         if (elect_one()) mma_commit(bar_acc + 8 * s);  // accumulator of this MMA complete
         __syncwarp();
+        FPROF_SINCE(10, _tm);
+        FPROF_COUNT(12);
       }
       cur.next(E);
       swap2(cur, oth);
@@ -377,6 +424,7 @@ mlp_fwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
       float* encd = s_encd + s * kMaxRaysPerTile * 32;
       float* hpart = s_hpart + s * 2 * 128 * 4;
 
+      FPROF_MARK(_te0);
       if (e == 0) {
         // ================= new tile: encodings of this row -> operand tile (value / 16), the two halves split the
         // frequencies
@@ -386,10 +434,11 @@ mlp_fwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
         ts.valid = ts.pt < P;
         if (!ts.valid) ts.pt = P - 1;
         const int64_t p0 = ts.p0, pt = ts.pt;
-        const int64_t ray = pt / S;
-        const int64_t first_ray = p0 / S;
+        // fewer than 2^31 points per call (checked on the host): 32-bit divisions instead of emulated 64-bit ones
+        const int64_t ray = (int64_t)((uint32_t)pt / (uint32_t)S);
+        const int64_t first_ray = (int64_t)((uint32_t)p0 / (uint32_t)S);
         const int64_t last_pt = (p0 + kTileRows - 1 < P) ? p0 + kTileRows - 1 : P - 1;
-        const int n_rays_tile = (int)(last_pt / S - first_ray) + 1;
+        const int n_rays_tile = (int)((uint32_t)last_pt / (uint32_t)S) - (int)first_ray + 1;
         ts.ray_slot = (int)(ray - first_ray);
         if (kTrain) {  // the previous tile's encoding store must have finished reading this buffer
           if (gtid == 0) bulk_wait_read();
@@ -430,11 +479,10 @@ mlp_fwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
           }
           epi_bar();
           const GemmLayer& gd = p.g[p.n_gemm - 1];
-          const float* wv = blob + gd.wt_off + (size_t)gd.k_h * gd.n;  // rows k_h.. of Wt[k][n]
           for (int i = gtid; i < n_rays_tile * gd.n; i += kEpiThreads) {
             const int jr = i / gd.n, n = i - jr * gd.n;
             float a = 0.f;
-            for (int k = 0; k < p.dim_dir; ++k) a = fmaf(encd[jr * 32 + k], wv[k * gd.n + n], a);
+            for (int k = 0; k < p.dim_dir; ++k) a = fmaf(encd[jr * 32 + k], s_wv[k * gd.n + n], a);
             viewb[jr * 64 + n] = fmaf(a, kActScale * kLoScale, s_bias[gd.cum_n + n]);  // per-ray bias of layers_dir[0] (x 2048 / 16)
           }
         }
@@ -445,6 +493,8 @@ mlp_fwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
           bulk_s2g(reinterpret_cast<uint8_t*>(stash + (size_t)P_pad * p.enc_cum[0]) + (size_t)ts.tile * tile_bytes(enc_w),
                    e_hi, (uint32_t)tile_bytes(enc_w));
         mbar_arrive(bar_a + 8 * s);
+        FPROF_SINCE(4, _te0);
+        FPROF_COUNT(6);
         return;
       }
 
@@ -466,7 +516,7 @@ mlp_fwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
       if (kTrain && valid)
         mask_row = reinterpret_cast<uint32_t*>(stash) + (size_t)P_pad * (p.mask_base + g.mask_cum) + (size_t)pt * (g.n >> 5);
 
-      mbar_wait(bar_acc + 8 * s, ts.acc_phase);
+      FPROF_SCOPE(0, mbar_wait(bar_acc + 8 * s, ts.acc_phase));
       ts.acc_phase ^= 1;
       tc_fence_after();
 
@@ -488,14 +538,17 @@ mlp_fwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
         for (int ch = 0; ch < nch; ++ch) {
           const int c0 = 64 * ch + 32 * half;
           uint32_t v[32];
-          tmem_ld32(t_acc + c0, v);
-          tmem_wait_ld();
+#if defined(NERFB200_EXP) && NERFB200_EXP == 1   // timing experiment: epilogue without its arithmetic (results are garbage)
+          continue;
+#endif
+          FPROF_SCOPE(1, { tmem_ld32(t_acc + c0, v); tmem_wait_ld(); });
           ca.mword_out = mask_row ? mask_row + (c0 >> 5) : nullptr;
           ca.tmem_hi = t_ahi + c0 / 2;  // two fp16 per tensor-memory column
           ca.tmem_lo = t_alo + c0 / 2;
-          epilogue_chunk<kTrain>(v, c0, ca, hacc);
+          FPROF_SCOPE(2, epilogue_chunk<kTrain>(v, c0, ca, hacc));
         }
       }
+      FPROF_MARK(_te1);
 
       if (hsel >= 0 && half == 1)
         *reinterpret_cast<float4*>(hpart + (hsel * 128 + row) * 4) = make_float4(hacc[0], hacc[1], hacc[2], hacc[3]);
@@ -506,6 +559,7 @@ mlp_fwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
       } else {
         tc_fence_before();
       }
+      FPROF_SINCE(3, _te1);
       if (hsel >= 0) {
         epi_bar();  // head partials in hpart
         if (half == 0 && valid) {
@@ -517,6 +571,8 @@ mlp_fwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
             if (c < hn) raw[pt * 4 + hcol + c] = tot[c];
         }
       }
+      FPROF_SINCE(5, _te0);
+      FPROF_COUNT(7);
     };
 
     const int n_mine = s ? seq.c1.n : seq.c0.n;
@@ -529,6 +585,9 @@ mlp_fwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
 
   tc_fence_before();
   __syncthreads();
+#ifdef NERFB200_PROF
+  if (blockIdx.x == 0 && threadIdx.x < 24) g_prof_fwd[threadIdx.x] += s_prof[threadIdx.x];
+#endif
   if (warp == kMmaWarp) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols));
 }
 

@@ -221,8 +221,9 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
                  "r"(kTmemColsB));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
-  for (int i = tid; i < hw1; i += kThreadsB) s_headw[i] = blob[p.h[0].w_off + i];
-  for (int i = tid; i < hw2; i += kThreadsB) s_headw[hw1 + i] = blob[p.h[1].w_off + i];
+  // head weights at the chain accumulator's 2^11 scale (the epilogue works on Y = 2048 y, tc_common.cuh split_f16x2_y)
+  for (int i = tid; i < hw1; i += kThreadsB) s_headw[i] = blob[p.h[0].w_off + i] * kLoScale;
+  for (int i = tid; i < hw2; i += kThreadsB) s_headw[hw1 + i] = blob[p.h[1].w_off + i] * kLoScale;
   for (int i = tid; i < p.enc_cum[0] + 8; i += kThreadsB) s_bgrad[i] = 0.f;
   for (int i = tid; i < 64 * 28; i += kThreadsB) s_dgrad[i] = 0.f;
   for (int i = tid; i < kMaxRays * 32; i += kThreadsB) s_encd[i] = 0.f;
@@ -596,9 +597,9 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
           for (int ch = 0; ch < 2; ++ch) {
             if (ch < nch) {
               const int c0 = 64 * ch + 32 * half;
-              float y[32];
+              float y[32];  // Y = 2048 x (pre-activation gradient), the accumulator's own scale
 #pragma unroll
-              for (int q = 0; q < 32; ++q) y[q] = has_mma ? __uint_as_float(v[ch][q]) * kLoInv : 0.f;
+              for (int q = 0; q < 32; ++q) y[q] = has_mma ? __uint_as_float(v[ch][q]) : 0.f;
               if (hn > 0) {
                 for (int c = 0; c < hn; ++c) {
                   const float dd = dr[(hcol + c) & 3];
@@ -618,7 +619,7 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
               for (int q = 0; q < 32; q += 2) {
                 const float y0 = (mword & (1u << q)) ? y[q] : 0.f;
                 const float y1 = (mword & (2u << q)) ? y[q + 1] : 0.f;
-                split_f16x2(y0, y1, hi[ch][q >> 1], lo[ch][q >> 1]);
+                split_f16x2_y(y0, y1, y0 * kLoInv, y1 * kLoInv, hi[ch][q >> 1], lo[ch][q >> 1]);
               }
             }
           }

@@ -47,11 +47,13 @@ constexpr int kWStage = 96 * 128;                 // one k-step of a 128-wide la
 constexpr int kMaxWStages = 6;
 constexpr int kGBytes = 65536;                    // G tile: hi block 32 KB, lo block 32 KB (128 features)
 constexpr int kXBytes = 65536;                    // activation tile of the running job
-constexpr int kStgBytes = 8192;                   // staging chunk: 128 rows x 16 fp32; two per column half (double buffer)
+constexpr int kStgBytes = 16384;                  // staging chunk: 128 rows x 32 fp32; two alternate
 constexpr int kIndBytes = 4096;                   // ray-indicator tile: 128 points x 16 "features" (hi only)
 constexpr int kMaxRays = 10;
 constexpr uint32_t kTmemColsB = 512;
-constexpr uint32_t kColAcc = 0, kColMain = 128, kMainStride = 144, kIndOff = 128, kColSecond = 416, kColHead0 = 480;
+// tensor memory: [0,128) chain accumulator, [128,192) / [192,256) the chain's A operand (G tile, hi / lo, two fp16 per
+// column), [256,400) main job (128) + indicator sums (16), [400,464) second job, [464,496) the heads' jobs
+constexpr uint32_t kColAcc = 0, kColAhi = 128, kColAlo = 192, kColMain = 256, kIndOff = 128, kColSecond = 400, kColHead0 = 464;
 constexpr int kSmemLimitB = 232448 - 1024;
 
 struct SmemMapB {
@@ -62,7 +64,7 @@ __host__ __device__ inline SmemMapB smem_map_b(const Plan& p) {
   int off = 0;
   m.g = off;      off += kGBytes;
   m.x = off;      off += kXBytes;
-  m.stg = off;    off += 4 * kStgBytes;
+  m.stg = off;    off += 2 * kStgBytes;
   m.ind = off;    off += kIndBytes;
   m.dtile = off;  off += 2 * kIndBytes;           // d_raw as a 16-column operand tile (hi block, lo block)
   m.headw = off;  off += (4 * 128 + 3 * 64 + 16) * 4;
@@ -86,9 +88,9 @@ struct BwdJob {
   int src;
   int n_b;       // columns = width of the B tile (multiple of 16)
   int col;       // tensor-memory column of the accumulator (main jobs: of buffer 0; + kMainStride for odd layers)
-  int dbuf;      // 1: double-buffered by layer parity
+  int dbuf;      // unused (the accumulators are single-buffered since the chain's A operand took their columns)
   int row0, nrows;  // accumulator rows that carry gradients
-  int gb_off;    // float offset of this job's block in the gradient blob: [n_b / 16 chunks][128 rows][16]
+  int gb_off;    // float offset of this job's block in the gradient blob: [n_b / 32 chunks][128 rows][32] (16 wide: one chunk of 16)
   int dst_head;  // -1: rows are output features of gemm layer `dst`; else head index, rows row0.. are its outputs
   int dst;       // gemm index
   int dst_col0;  // first input column of the destination weight this block covers
@@ -111,7 +113,7 @@ __host__ __device__ inline int bwd_jobs(const Plan& p, int e, BwdJob* out, int* 
       j.src_enc = src_enc; j.src = src; j.n_b = n_b; j.col = col; j.row0 = row0; j.nrows = nrows;
       j.gb_off = gb; j.dst_head = dst_head; j.dst = dst; j.dst_col0 = dst_col0; j.ncols = ncols; j.kind = kind;
       j.dbuf = (col == (int)kColMain) ? 1 : 0;
-      if (kind == 0) gb += (n_b / 16) * 128 * 16;
+      if (kind == 0) gb += ((n_b + 31) / 32) * 128 * 32;
     };
     if (g.k_h > 0) add(0, g.src, g.k_h, (int)kColMain, 0, g.n, -1, t, 0, g.k_h, 0);
     if (g.k_enc > 0 && g.enc_sel == 0)
@@ -183,14 +185,15 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
   uint64_t* w_full = bars;                      // [kMaxWStages]
   uint64_t* w_empty = bars + kMaxWStages;       // [kMaxWStages]
   uint64_t* bar_acc = bars + 2 * kMaxWStages;   // chain MMA complete
-  uint64_t* bar_g = bar_acc + 1;                // G tile (+ indicator tile) written, chain accumulator drained
+  uint64_t* bar_g = bar_acc + 1;                // G tile (+ indicator tile) written to shared memory (the jobs' A operand)
   uint64_t* xh_full = bar_g + 1;
   uint64_t* xl_full = xh_full + 1;
   uint64_t* xh_free = xl_full + 1;
   uint64_t* xl_free = xh_free + 1;
   uint64_t* job_done = xl_free + 1;             // [2][kMaxJobs]: job i of a layer of that parity complete
-  uint64_t* acc_free = job_done + 2 * kMaxJobs; // [2]: the drain is done with the accumulators of that parity
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(acc_free + 2);
+  uint64_t* acc_free = job_done + 2 * kMaxJobs; // [0]: the drain is done with the layer's accumulators
+  uint64_t* bar_a = acc_free + 2;               // the chain's A operand (this layer's G, hi / lo) is in tensor memory
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_a + 1);
   const uint32_t n_stages = (uint32_t)mp.n_stages;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -206,6 +209,7 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
     }
     mbar_init(bar_acc, 1);
     mbar_init(bar_g, kEpi);
+    mbar_init(bar_a, kEpi);
     mbar_init(xh_full, 1);
     mbar_init(xl_full, 1);
     mbar_init(xh_free, 1);
@@ -288,11 +292,10 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
   } else if (warp == 8) {
     // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
     Pipe pp;
-    uint32_t g_ph = 0, x_ph = 0, gev = 0;  // gev: layers processed so far (selects the accumulator buffer)
-    uint32_t free_ph[2] = {0u, 0u};
-    const uint32_t t_acc = tmem + kColAcc;
+    uint32_t g_ph = 0, a_ph = 0, x_ph = 0, gev = 0;  // gev: layers processed so far
+    uint32_t free_ph = 0;
+    const uint32_t t_acc = tmem + kColAcc, t_ahi = tmem + kColAhi, t_alo = tmem + kColAlo;
     // every descriptor is built ONCE; the loops only advance start-address fields (tc_common.cuh desc_adv)
-    const uint64_t g_hi_k = make_desc(smem_u32(sG), 128, 2048), g_lo_k = desc_adv(g_hi_k, 32768);    // K-major view (chain A)
     const uint64_t g_hi_m = make_desc(smem_u32(sG), 2048, 128), g_lo_m = desc_adv(g_hi_m, 32768);    // MN-major view (job A)
     const uint64_t ind_d = make_desc(smem_u32(sInd), 256, 128);
     const uint64_t d_hi_d = make_desc(smem_u32(sD), 256, 128), d_lo_d = desc_adv(d_hi_d, kIndBytes);
@@ -300,12 +303,13 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
     for (int it = 0; it < my_tiles; ++it)
       for (int e = 0; e < E; ++e, ++gev) {
         const GemmLayer& g = p.g[E - 1 - e];
-        PROF_SCOPE(10, mbar_wait(bar_g, g_ph));
-        g_ph ^= 1;
+        PROF_SCOPE(8, mbar_wait(bar_a, a_ph));
+        a_ph ^= 1;
         tc_fence_after();
         if (e + 1 < E) {
-          // ---- chain: accumulator[p][k] = 2^11 sum_n G_t[p][n] W_t[n][k], N = k_h, K = n; A = the G tile's K-major
-          // view (rows = points: SBO 16 * 128; K = features: LBO 128; one k-step = 2 feature blocks = 256 bytes)
+          // ---- chain: accumulator[p][k] = 2^11 sum_n G_t[p][n] W_t[n][k], N = k_h, K = n; A = this layer's G from
+          // TENSOR memory (the epilogue stores the hi / lo registers there first: the chain neither waits for the
+          // shared-memory tile nor reads it -- an SS MMA at N = 128 alone saturates the shared-memory port)
           const uint32_t idesc = make_idesc_f16(g.k_h);
           const uint32_t slab_b = 16u * (uint32_t)g.k_h;
           const uint64_t b_ring = make_desc(smem_u32(sm + mp.ring), slab_b, 128);
@@ -316,10 +320,9 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
               const uint64_t b_hs = desc_adv(b_ring, pp.stage * (uint32_t)kWStage);
               const uint64_t b_h = desc_adv(b_hs, 2 * slab_b);
               const uint64_t b_l = desc_adv(b_hs, 4 * slab_b);
-              const uint64_t a_hi = desc_adv(g_hi_k, ks * 256), a_lo = desc_adv(g_lo_k, ks * 256);
-              mma_ss_f16(t_acc, a_hi, b_hs, idesc, ks > 0 ? 1u : 0u);
-              mma_ss_f16(t_acc, a_lo, b_h, idesc, 1u);
-              mma_ss_f16(t_acc, a_hi, b_l, idesc, 1u);
+              mma_ts_f16(t_acc, t_ahi + 8 * ks, b_hs, idesc, ks > 0 ? 1u : 0u);
+              mma_ts_f16(t_acc, t_alo + 8 * ks, b_h, idesc, 1u);
+              mma_ts_f16(t_acc, t_ahi + 8 * ks, b_l, idesc, 1u);
               mma_commit(&w_empty[pp.stage]);
             }
             __syncwarp();
@@ -328,10 +331,14 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
           if (elect_one()) mma_commit(bar_acc);
           __syncwarp();
         }
-        // ---- weight-gradient jobs of this event; the accumulators of this parity were last used two layers ago
-        if (gev >= 2) {
-          PROF_SCOPE(13, mbar_wait(&acc_free[gev & 1u], free_ph[gev & 1u]));
-          free_ph[gev & 1u] ^= 1;
+        // ---- weight-gradient jobs of this event: A = the G tile in shared memory (MN-major view); the accumulators
+        // are single-buffered: the drain must be done with the previous layer's
+        PROF_SCOPE(10, mbar_wait(bar_g, g_ph));
+        g_ph ^= 1;
+        tc_fence_after();
+        if (gev >= 1) {
+          PROF_SCOPE(13, mbar_wait(&acc_free[0], free_ph));
+          free_ph ^= 1;
           tc_fence_after();
         }
         const int nj = bp.n_jobs[e];
@@ -339,7 +346,7 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
           const BwdJob& jq = bp.jobs[e][i];
           const int w = jq.n_b;
           const uint32_t fstr = (uint32_t)(w >> 3) * 128u;  // bytes between 8-point blocks of the activation tile
-          const uint32_t d = tmem + (uint32_t)jq.col + (jq.dbuf ? (gev & 1u) * kMainStride : 0u);
+          const uint32_t d = tmem + (uint32_t)jq.col;
           const uint64_t x_hi_d = make_desc(x_hi_a, fstr, 128), x_lo_d = make_desc(x_lo_a, fstr, 128);  // MN-major views
           if (jq.kind == 1) {
             // head job: A = activation tile (rows = its features: SBO 128, K = points: LBO fstr), B = d_raw tile (N = 16)
@@ -365,7 +372,7 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
               for (int ks = 1; ks < 8; ++ks)
                 mma_ss_f16(d, desc_adv(x_hi_d, ks * 2 * fstr), desc_adv(d_hi_d, ks * 512), id16, 1u);
               mma_commit(xh_free);
-              mma_commit(&job_done[(gev & 1u) * kMaxJobs + i]);
+              mma_commit(&job_done[i]);
             }
             __syncwarp();
             continue;
@@ -405,7 +412,7 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
               for (int ks = 1; ks < 8; ++ks)
                 mma_ss_f16(di, desc_adv(g_hi_m, ks * 4096), desc_adv(ind_d, ks * 512), id16, 1u);
             }
-            mma_commit(&job_done[(gev & 1u) * kMaxJobs + i]);
+            mma_commit(&job_done[i]);
           }
           __syncwarp();
         }
@@ -417,24 +424,23 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
     const int row = tid - kDrainWarp0 * 32;
     const uint32_t lane_base = ((uint32_t)((warp & 3) * 32)) << 16;
     float* stg = reinterpret_cast<float*>(sm + mp.stg);
-    uint32_t stg_n = 0, gev = 0;  // chunks staged so far (selects one of the four staging buffers); layers drained
-    uint32_t job_ph[2][kMaxJobs] = {{0u, 0u, 0u}, {0u, 0u, 0u}};
+    uint32_t stg_n = 0, gev = 0;  // chunks staged so far (selects one of the two staging buffers); layers drained
+    uint32_t job_ph[kMaxJobs] = {0u, 0u, 0u};
     for (int it = 0; it < my_tiles; ++it) {
       const int64_t tile = blockIdx.x + (int64_t)it * gridDim.x;
       const int64_t p0 = tile * kTileRows;
       const int64_t last_pt = (p0 + kTileRows - 1 < P) ? p0 + kTileRows - 1 : P - 1;
       const int n_rays_tile = (int)(last_pt / S - p0 / S) + 1;
       for (int de = 0; de < E; ++de, ++gev) {
-        const uint32_t parity = gev & 1u;
         const int nj = bp.n_jobs[de];
         const GemmLayer& g = p.g[E - 1 - de];
         for (int i = 0; i < nj; ++i) {
-          PROF_SCOPE(3, mbar_wait(&job_done[parity * kMaxJobs + i], job_ph[parity][i]));
-          job_ph[parity][i] ^= 1;
+          PROF_SCOPE(3, mbar_wait(&job_done[i], job_ph[i]));
+          job_ph[i] ^= 1;
           tc_fence_after();
           const float us = s_us[it & 1];  // written by the epilogue before this tile's first job could be issued
           const BwdJob& j = bp.jobs[de][i];
-          const uint32_t jcol = (uint32_t)j.col + (j.dbuf ? parity * kMainStride : 0u);
+          const uint32_t jcol = (uint32_t)j.col;
           if (j.kind == 1) {
             // head job: lane = input feature k of the head, columns = d_raw channels: dW_head[c][k], a handful of atomics
             uint32_t v16[16];
@@ -446,25 +452,28 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
                 atomicAdd(flat_grad + h.flat_w + (size_t)c * h.k + row, __uint_as_float(v16[(h.out_col + c) & 15]) * us);
             continue;
           }
-          // 16-column chunks through four rotating staging buffers: a buffer is rewritten only after the bulk
-          // reduction issued four chunks ago has finished reading it
-          const int nchunk = j.n_b >> 4;
+          // 32-column chunks through two alternating 16 KB staging buffers: a buffer is rewritten only after the bulk
+          // reduction issued two chunks ago has finished reading it.  Rows are 128 bytes; the eight 16-byte pieces of a
+          // row are XOR-swizzled by (row & 7) so that a warp's stores spread over all banks.  (Tried and rejected:
+          // red.global.add.v4.f32 straight from the registers -- 1.3 cycles per lane on the SM side and every CTA hits
+          // the same L2 lines: 2.37 -> 2.76 ms.)  A 48-wide job's second chunk carries 16 columns of padding.
+          const int nchunk = (j.n_b + 31) >> 5;
           for (int c = 0; c < nchunk; ++c) {
-            uint32_t v[16];
-            tmem_ld16(tmem + lane_base + jcol + 16 * c, v);
-            float* sb = stg + (stg_n & 3u) * (kStgBytes / 4);
-            if (row == 0) asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory");
+            uint32_t v[32];
+            tmem_ld32(tmem + lane_base + jcol + 32 * c, v);
+            float* sb = stg + (stg_n & 1u) * (kStgBytes / 4);
+            if (row == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
             bar_half(0);
             tmem_wait_ld();
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-              *reinterpret_cast<float4*>(sb + row * 16 + ((q ^ ((row >> 1) & 3)) << 2)) =
+            for (int q = 0; q < 8; ++q)
+              *reinterpret_cast<float4*>(sb + row * 32 + ((q ^ (row & 7)) << 2)) =
                   make_float4(__uint_as_float(v[4 * q]) * us, __uint_as_float(v[4 * q + 1]) * us,
                               __uint_as_float(v[4 * q + 2]) * us, __uint_as_float(v[4 * q + 3]) * us);
             fence_proxy_async();
             bar_half(0);
             if (row == 0)
-              bulk_reduce_add_f32(gblob + j.gb_off + (size_t)c * 2048 + j.row0 * 16, sb + j.row0 * 16, (uint32_t)j.nrows * 64u);
+              bulk_reduce_add_f32(gblob + j.gb_off + (size_t)c * 4096 + j.row0 * 32, sb + j.row0 * 32, (uint32_t)j.nrows * 128u);
             ++stg_n;
           }
           if (i == 0) {
@@ -491,7 +500,7 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
           }
         }
         tc_fence_before();
-        mbar_arrive(&acc_free[parity]);
+        mbar_arrive(&acc_free[0]);
       }
     }
     if (row == 0) bulk_wait_all();
@@ -516,14 +525,14 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
     const uint32_t lane_base = ((uint32_t)((warp & 3) * 32)) << 16;
     const uint32_t t_acc = tmem + lane_base + kColAcc;
     uint32_t acc_ph = 0, gev = 0;  // gev: layers processed so far (parity of the job barriers)
-    uint32_t job_ph[2][kMaxJobs] = {{0u, 0u, 0u}, {0u, 0u, 0u}};
+    uint32_t job_ph[kMaxJobs] = {0u, 0u, 0u};
     int prev_e = -1;  // the previous layer: its jobs must have finished reading the G tile before this layer's is written
 
-    auto wait_jobs = [&](const int de, const uint32_t parity) {  // every job of that layer complete
+    auto wait_jobs = [&](const int de) {  // every job of that layer complete
       const int nj = bp.n_jobs[de];
       for (int i = 0; i < nj; ++i) {
-        PROF_SCOPE(3, mbar_wait(&job_done[parity * kMaxJobs + i], job_ph[parity][i]));
-        job_ph[parity][i] ^= 1;
+        PROF_SCOPE(3, mbar_wait(&job_done[i], job_ph[i]));
+        job_ph[i] ^= 1;
       }
       tc_fence_after();
     };
@@ -629,8 +638,24 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
         const long long _tb = clock64();
         if (tid == 0 && blockIdx.x == 0) g_prof[1] += (unsigned long long)(_tb - _ta);
 #endif
+        // ---- the chain's A operand: the same hi / lo registers -> tensor memory (two fp16 per column), then the chain
+        // MMA of this layer may start; it has nothing to do with the shared-memory tile written below
+        {
+          const uint32_t t_ahi = tmem + lane_base + kColAhi, t_alo = tmem + lane_base + kColAlo;
+#pragma unroll
+          for (int ch = 0; ch < 2; ++ch) {
+            if (ch < nch) {
+              const int c0 = 64 * ch + 32 * half;
+              tmem_st16(t_ahi + c0 / 2, hi[ch]);
+              tmem_st16(t_alo + c0 / 2, lo[ch]);
+            }
+          }
+          tmem_wait_st();
+          tc_fence_before();
+          mbar_arrive(bar_a);
+        }
         // the previous layer's jobs read the G tile: they must be complete before it is overwritten
-        if (prev_e >= 0) wait_jobs(prev_e, (gev - 1u) & 1u);
+        if (prev_e >= 0) wait_jobs(prev_e);
 #ifdef NERFB200_PROF
         const long long _tc = clock64();
 #endif
@@ -716,8 +741,8 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
   if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemColsB));
 }
 
-// gradient blob -> flat (torch-layout) gradient vector: every job block is [chunk][row][16 floats] with the four
-// 16-byte pieces of a row XOR-swizzled by ((row >> 1) & 3) (the staging tile's bank-conflict-free layout)
+// gradient blob -> flat (torch-layout) gradient vector: every job block is [chunk][row][32 floats] with the eight
+// 16-byte pieces of a row XOR-swizzled by (row & 7) (the staging tile's bank-conflict-free layout)
 __global__ void unpack_grad_kernel(const __grid_constant__ Plan p, const __grid_constant__ BwdPlan bp,
                                    const float* __restrict__ gblob, float* __restrict__ flat_grad) {
   const int gb_total = bp.gb_total;
@@ -728,12 +753,12 @@ __global__ void unpack_grad_kernel(const __grid_constant__ Plan p, const __grid_
       for (int i = 0; i < nj && !done; ++i) {
         const BwdJob& j = bp.jobs[e][i];
         if (j.kind != 0) continue;
-        const int sz = (j.n_b / 16) * 2048;
+        const int sz = ((j.n_b + 31) / 32) * 4096;
         if (idx < j.gb_off || idx >= j.gb_off + sz) continue;
         done = true;
         const int r = idx - j.gb_off;
-        const int c = r >> 11, rr = (r >> 4) & 127, w = r & 15;
-        const int col = 16 * c + ((((w >> 2) ^ ((rr >> 1) & 3)) << 2) | (w & 3));
+        const int c = r >> 12, rr = (r >> 5) & 127, w = r & 31;
+        const int col = 32 * c + ((((w >> 2) ^ (rr & 7)) << 2) | (w & 3));
         if (rr < j.row0 || rr >= j.row0 + j.nrows || col >= j.ncols) break;
         const float v = gblob[idx];
         const GemmLayer& g = p.g[j.dst];

@@ -71,7 +71,7 @@ __host__ __device__ inline SmemMapB smem_map_b(const Plan& p) {
   m.bgrad = off;  off += (p.enc_cum[0] + 8) * 4;   // bias gradients of every gemm layer + the heads' (8)
   m.dgrad = off;  off += 64 * 28 * 4;              // direction-encoding part of dW(layers_dir[0]): [n][e], e < 28
   m.encd = off;   off += kMaxRays * 32 * 4;
-  m.misc = off;   off += 64;
+  m.misc = off;   off += 256;              // tile maxima / unscale factors (+ the development build's cycle counters)
   m.bars = off;   off += 256;
   off = (off + 1023) & ~1023;
   m.ring = off;
@@ -152,11 +152,19 @@ using namespace tcb;
 // Development build only (make EXTRA=-DNERFB200_PROF): CTA 0 adds up the cycles its roles spend in each phase.
 #ifdef NERFB200_PROF
 __device__ unsigned long long g_prof[32];
-#define PROF_T0() const long long _pt0 = clock64()
-#define PROF_ADD(i) do { if (blockIdx.x == 0) g_prof[i] += (unsigned long long)(clock64() - _pt0); } while (0)
-#define PROF_SCOPE(i, stmt) do { const long long _ps = clock64(); stmt; if (blockIdx.x == 0) g_prof[i] += (unsigned long long)(clock64() - _ps); } while (0)
+// counters live in shared memory (lane 0 of warps 0, 8, 9, 10, 12 of CTA 0 record), flushed to g_prof when the kernel ends
+#define PROF_DECL uint32_t* s_prof = reinterpret_cast<uint32_t*>(sm + mp.misc + 64); if (threadIdx.x < 32) s_prof[threadIdx.x] = 0u;
+#define PROF_ON (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (threadIdx.x < 32 || (threadIdx.x >= 256 && threadIdx.x < 352) || (threadIdx.x >= 384 && threadIdx.x < 416)))
+#define PROF_SCOPE(i, stmt) do { const long long _ps = clock64(); stmt; if (PROF_ON) s_prof[i] += (uint32_t)(clock64() - _ps); } while (0)
+#define PROF_MARK(name) const long long name = clock64()
+#define PROF_SINCE(i, name) do { if (PROF_ON) s_prof[i] += (uint32_t)(clock64() - name); } while (0)
+#define PROF_FLUSH do { __syncthreads(); if (blockIdx.x == 0 && threadIdx.x < 32) g_prof[threadIdx.x] += s_prof[threadIdx.x]; } while (0)
 #else
+#define PROF_DECL
 #define PROF_SCOPE(i, stmt) do { stmt; } while (0)
+#define PROF_MARK(name)
+#define PROF_SINCE(i, name)
+#define PROF_FLUSH
 #endif
 
 __device__ __forceinline__ void bar_half(int half) {  // the 128 threads of one column half
@@ -171,6 +179,7 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const SmemMapB mp = smem_map_b(p);
+  PROF_DECL
   uint8_t* sG = sm + mp.g;
   uint8_t* sX = sm + mp.x;
   uint8_t* sInd = sm + mp.ind;
@@ -303,6 +312,7 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
     for (int it = 0; it < my_tiles; ++it)
       for (int e = 0; e < E; ++e, ++gev) {
         const GemmLayer& g = p.g[E - 1 - e];
+        PROF_MARK(_tm0);
         PROF_SCOPE(8, mbar_wait(bar_a, a_ph));
         a_ph ^= 1;
         tc_fence_after();
@@ -333,6 +343,8 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
         }
         // ---- weight-gradient jobs of this event: A = the G tile in shared memory (MN-major view); the accumulators
         // are single-buffered: the drain must be done with the previous layer's
+        PROF_SINCE(14, _tm0);
+        PROF_MARK(_tm1);
         PROF_SCOPE(10, mbar_wait(bar_g, g_ph));
         g_ph ^= 1;
         tc_fence_after();
@@ -400,7 +412,11 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
             for (int ks = 1; ks < 8; ++ks)
               mma_ss_f16(d, desc_adv(g_hi_m, ks * 4096), desc_adv(x_hi_d, ks * 2 * fstr), id_mn, 1u);
             mma_commit(xh_free);
+#if defined(NERFB200_EXPB) && (NERFB200_EXPB & 2)   // timing experiment: no indicator MMAs
+            if (false) {
+#else
             if (i == 0) {
+#endif
               // indicator job: sums[n][j] = sum over the points of ray j of the tile of G[p][n] (16 columns)
               const uint32_t id16 = make_idesc_f16_mn(16, 1, 1);
               const uint32_t di = d + kIndOff;
@@ -416,6 +432,7 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
           }
           __syncwarp();
         }
+        PROF_SINCE(15, _tm1);
       }
   }
   } else if (warp >= kDrainWarp0) {
@@ -458,9 +475,14 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
           // red.global.add.v4.f32 straight from the registers -- 1.3 cycles per lane on the SM side and every CTA hits
           // the same L2 lines: 2.37 -> 2.76 ms.)  A 48-wide job's second chunk carries 16 columns of padding.
           const int nchunk = (j.n_b + 31) >> 5;
+          PROF_MARK(_td0);
           for (int c = 0; c < nchunk; ++c) {
             uint32_t v[32];
             tmem_ld32(tmem + lane_base + jcol + 32 * c, v);
+#if defined(NERFB200_EXPB) && (NERFB200_EXPB & 1)   // timing experiment: drain without staging / reduction
+            tmem_wait_ld();
+            continue;
+#endif
             float* sb = stg + (stg_n & 1u) * (kStgBytes / 4);
             if (row == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
             bar_half(0);
@@ -476,6 +498,7 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
               bulk_reduce_add_f32(gblob + j.gb_off + (size_t)c * 4096 + j.row0 * 32, sb + j.row0 * 32, (uint32_t)j.nrows * 128u);
             ++stg_n;
           }
+          PROF_SINCE(6, _td0);
           if (i == 0) {
             // indicator sums of this layer: bias gradient (all rays) and, for layers_dir[0], the direction-encoding part
             uint32_t v16[16];
@@ -531,7 +554,7 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
     auto wait_jobs = [&](const int de) {  // every job of that layer complete
       const int nj = bp.n_jobs[de];
       for (int i = 0; i < nj; ++i) {
-        PROF_SCOPE(3, mbar_wait(&job_done[i], job_ph[i]));
+        PROF_SCOPE(2, mbar_wait(&job_done[i], job_ph[i]));
         job_ph[i] ^= 1;
       }
       tc_fence_after();
@@ -587,9 +610,7 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
           acc_ph ^= 1;
           tc_fence_after();
         }
-#ifdef NERFB200_PROF
-        const long long _ta = clock64();
-#endif
+        PROF_MARK(_ta);
         // ---------------- part A: G_t of this row -> hi / lo registers and tensor memory ----------------
         // (both column chunks are pulled out of the accumulator before any arithmetic; the head term only exists for
         // the two layers a head reads and stays out of the hot loop)
@@ -634,12 +655,10 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
           }
         }
         tc_fence_before();
-#ifdef NERFB200_PROF
-        const long long _tb = clock64();
-        if (tid == 0 && blockIdx.x == 0) g_prof[1] += (unsigned long long)(_tb - _ta);
-#endif
+        PROF_SINCE(1, _ta);
         // ---- the chain's A operand: the same hi / lo registers -> tensor memory (two fp16 per column), then the chain
         // MMA of this layer may start; it has nothing to do with the shared-memory tile written below
+        PROF_MARK(_tst);
         {
           const uint32_t t_ahi = tmem + lane_base + kColAhi, t_alo = tmem + lane_base + kColAlo;
 #pragma unroll
@@ -654,11 +673,10 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
           tc_fence_before();
           mbar_arrive(bar_a);
         }
+        PROF_SINCE(4, _tst);
         // the previous layer's jobs read the G tile: they must be complete before it is overwritten
         if (prev_e >= 0) wait_jobs(prev_e);
-#ifdef NERFB200_PROF
-        const long long _tc = clock64();
-#endif
+        PROF_MARK(_tc);
 
         // ---------------- part B: the held registers -> G tile (MN-major A operand of this event's jobs) ----------------
 #pragma unroll
@@ -726,9 +744,9 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
         }
         fence_proxy_async();
         mbar_arrive(bar_g);
+        PROF_SINCE(5, _tc);
 #ifdef NERFB200_PROF
-        const long long _td2 = clock64();
-        if (tid == 0 && blockIdx.x == 0) { g_prof[5] += (unsigned long long)(_td2 - _tc); g_prof[7] += 1; }
+        if (PROF_ON) s_prof[7] += 1;
 #endif
         prev_e = e;
         ++gev;
@@ -738,6 +756,7 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
 
   tc_fence_before();
   __syncthreads();
+  PROF_FLUSH;
   if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemColsB));
 }
 

@@ -33,9 +33,11 @@ torch.cuda.synchronize()
 lib.nerfb200_prof_read(buf, 0)
 v = list(buf)
 ev = max(v[7], 1)
-names = {0: "epi wait bar_acc", 1: "epi part A", 2: "epi drain total", 3: "  drain: wait job_done", 4: "  drain: barrier+reduce+wait_read",
-         5: "epi part B", 8: "mma wait bar_a", 9: "mma wait w_full", 10: "mma wait bar_g", 11: "mma wait xl_full", 12: "mma wait xh_full",
-         13: "mma wait slot0", 16: "xprod wait xl_free", 17: "xprod wait xh_free", 18: "wprod wait w_empty"}
+names = {0: "epi: wait bar_acc (chain done)", 1: "epi: part A (acc -> hi/lo registers)", 4: "epi: hi/lo -> tensor memory + arrive bar_a",
+         2: "epi: wait job_done (G tile free)", 5: "epi: part B (registers -> G tile)", 3: "drain: wait job_done", 6: "drain: chunk loops",
+         8: "mma: wait bar_a", 9: "mma: wait w_full", 10: "mma: wait bar_g", 11: "mma: wait xl_full", 12: "mma: wait xh_full",
+         13: "mma: wait acc_free", 14: "mma: chain section (incl. waits)", 15: "mma: jobs section (incl. waits)",
+         16: "xprod: wait xl_free", 17: "xprod: wait xh_free", 18: "wprod: wait w_empty"}
 print(f"kernel+unpack {e0.elapsed_time(e1):.3f} ms; events of CTA 0: {ev}")
 for k in sorted(names):
     print(f"  {names[k]:36s} {v[k] / ev:10.0f} cycles / event")

@@ -57,7 +57,7 @@ constexpr uint32_t kColAcc = 0, kColAhi = 128, kColAlo = 192, kColMain = 256, kI
 constexpr int kSmemLimitB = 232448 - 1024;
 
 struct SmemMapB {
-  int g, x, stg, ind, dtile, headw, bgrad, dgrad, encd, misc, bars, ring, total, n_stages;
+  int g, x, stg, ind, headw, bgrad, encd, misc, bars, ring, total, n_stages;
 };
 __host__ __device__ inline SmemMapB smem_map_b(const Plan& p) {
   SmemMapB m;
@@ -66,10 +66,8 @@ __host__ __device__ inline SmemMapB smem_map_b(const Plan& p) {
   m.x = off;      off += kXBytes;
   m.stg = off;    off += 2 * kStgBytes;
   m.ind = off;    off += kIndBytes;
-  m.dtile = off;  off += 2 * kIndBytes;           // d_raw as a 16-column operand tile (hi block, lo block)
   m.headw = off;  off += (4 * 128 + 3 * 64 + 16) * 4;
   m.bgrad = off;  off += (p.enc_cum[0] + 8) * 4;   // bias gradients of every gemm layer + the heads' (8)
-  m.dgrad = off;  off += 64 * 28 * 4;              // direction-encoding part of dW(layers_dir[0]): [n][e], e < 28
   m.encd = off;   off += kMaxRays * 32 * 4;
   m.misc = off;   off += 256;              // tile maxima / unscale factors (+ the development build's cycle counters)
   m.bars = off;   off += 256;
@@ -183,10 +181,8 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
   uint8_t* sG = sm + mp.g;
   uint8_t* sX = sm + mp.x;
   uint8_t* sInd = sm + mp.ind;
-  uint8_t* sD = sm + mp.dtile;
   float* s_headw = reinterpret_cast<float*>(sm + mp.headw);
   float* s_bgrad = reinterpret_cast<float*>(sm + mp.bgrad);
-  float* s_dgrad = reinterpret_cast<float*>(sm + mp.dgrad);
   float* s_encd = reinterpret_cast<float*>(sm + mp.encd);
   uint32_t* s_max = reinterpret_cast<uint32_t*>(sm + mp.misc);      // [2]: tile max of |d_raw| (alternating tiles)
   float* s_us = reinterpret_cast<float*>(sm + mp.misc) + 2;         // [2]: the tile's unscale factor, for the drain
@@ -238,10 +234,8 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
   for (int i = tid; i < hw1; i += kThreadsB) s_headw[i] = blob[p.h[0].w_off + i] * kLoScale;
   for (int i = tid; i < hw2; i += kThreadsB) s_headw[hw1 + i] = blob[p.h[1].w_off + i] * kLoScale;
   for (int i = tid; i < p.enc_cum[0] + 8; i += kThreadsB) s_bgrad[i] = 0.f;
-  for (int i = tid; i < 64 * 28; i += kThreadsB) s_dgrad[i] = 0.f;
   for (int i = tid; i < kMaxRays * 32; i += kThreadsB) s_encd[i] = 0.f;
   for (int i = tid; i < kGBytes / 16; i += kThreadsB) reinterpret_cast<uint4*>(sG)[i] = make_uint4(0u, 0u, 0u, 0u);
-  for (int i = tid; i < 2 * kIndBytes / 16; i += kThreadsB) reinterpret_cast<uint4*>(sD)[i] = make_uint4(0u, 0u, 0u, 0u);
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
@@ -307,7 +301,9 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
     // every descriptor is built ONCE; the loops only advance start-address fields (tc_common.cuh desc_adv)
     const uint64_t g_hi_m = make_desc(smem_u32(sG), 2048, 128), g_lo_m = desc_adv(g_hi_m, 32768);    // MN-major view (job A)
     const uint64_t ind_d = make_desc(smem_u32(sInd), 256, 128);
-    const uint64_t d_hi_d = make_desc(smem_u32(sD), 256, 128), d_lo_d = desc_adv(d_hi_d, kIndBytes);
+    // d_raw as a 16-column operand (heads' jobs, first layer of a tile): feature rows 64..79 of that layer's G tile
+    // (rows 64..67 carry d_raw, the rest is zero): MN-major view, 8-point blocks 2048 B apart
+    const uint64_t d_hi_d = make_desc(smem_u32(sG) + 1024, 2048, 128), d_lo_d = desc_adv(d_hi_d, 32768);
     const uint32_t x_hi_a = smem_u32(sX), x_lo_a = x_hi_a + 32768;
     for (int it = 0; it < my_tiles; ++it)
       for (int e = 0; e < E; ++e, ++gev) {
@@ -368,7 +364,7 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
             if (elect_one()) {
 #pragma unroll
               for (int ks = 0; ks < 8; ++ks)
-                mma_ss_f16(d, desc_adv(x_lo_d, ks * 2 * fstr), desc_adv(d_hi_d, ks * 512), id16, ks > 0 ? 1u : 0u);
+                mma_ss_f16(d, desc_adv(x_lo_d, ks * 2 * fstr), desc_adv(d_hi_d, ks * 4096), id16, ks > 0 ? 1u : 0u);
               mma_commit(xl_free);
             }
             __syncwarp();
@@ -378,11 +374,11 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
             if (elect_one()) {
 #pragma unroll
               for (int ks = 0; ks < 8; ++ks)
-                mma_ss_f16(d, desc_adv(x_hi_d, ks * 2 * fstr), desc_adv(d_lo_d, ks * 512), id16, 1u);
+                mma_ss_f16(d, desc_adv(x_hi_d, ks * 2 * fstr), desc_adv(d_lo_d, ks * 4096), id16, 1u);
               mma_ss_f16_scale11(d, x_hi_d, d_hi_d, id16);
 #pragma unroll
               for (int ks = 1; ks < 8; ++ks)
-                mma_ss_f16(d, desc_adv(x_hi_d, ks * 2 * fstr), desc_adv(d_hi_d, ks * 512), id16, 1u);
+                mma_ss_f16(d, desc_adv(x_hi_d, ks * 2 * fstr), desc_adv(d_hi_d, ks * 4096), id16, 1u);
               mma_commit(xh_free);
               mma_commit(&job_done[i]);
             }
@@ -441,6 +437,9 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
     const int row = tid - kDrainWarp0 * 32;
     const uint32_t lane_base = ((uint32_t)((warp & 3) * 32)) << 16;
     float* stg = reinterpret_cast<float*>(sm + mp.stg);
+    float dacc[28];  // direction-encoding part of dW(layers_dir[0]) for output feature `row` (< 64), whole kernel
+#pragma unroll
+    for (int k = 0; k < 28; ++k) dacc[k] = 0.f;
     uint32_t stg_n = 0, gev = 0;  // chunks staged so far (selects one of the two staging buffers); layers drained
     uint32_t job_ph[kMaxJobs] = {0u, 0u, 0u};
     for (int it = 0; it < my_tiles; ++it) {
@@ -511,14 +510,16 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
             if (row < g.n) s_bgrad[g.cum_n + row] += tot * su;
             if (de == 0 && p.use_viewdirs) {
               if (row >= 64 && row < 68) s_bgrad[p.enc_cum[0] + row - 64] += tot * su;  // d_rgb, d_sigma sums
-              if (row < g.n)
-                for (int k = 0; k < p.dim_dir; ++k) {
+#pragma unroll
+              for (int k = 0; k < 28; ++k) {
+                if (k < p.dim_dir) {
                   float a = 0.f;
 #pragma unroll
                   for (int q = 0; q < kMaxRays; ++q)
                     if (q < n_rays_tile) a = fmaf(__uint_as_float(v16[q]), s_encd[q * 32 + k], a);
-                  s_dgrad[row * 28 + k] += a * su;
+                  dacc[k] = fmaf(a, su, dacc[k]);
                 }
+              }
             }
           }
         }
@@ -534,9 +535,10 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
     if (p.use_viewdirs) {
       const GemmLayer& gd = p.g[p.n_gemm - 1];
       const int in_real = gd.k_h + gd.enc_real;
-      for (int i = row; i < gd.n * p.dim_dir; i += kDrainThreads) {
-        const int n = i / p.dim_dir, k = i - n * p.dim_dir;
-        atomicAdd(flat_grad + gd.flat_w + (size_t)n * in_real + gd.k_h + k, s_dgrad[n * 28 + k]);
+      if (row < gd.n) {
+#pragma unroll
+        for (int k = 0; k < 28; ++k)
+          if (k < p.dim_dir) atomicAdd(flat_grad + gd.flat_w + (size_t)row * in_real + gd.k_h + k, dacc[k]);
       }
       if (row < 3) atomicAdd(flat_grad + p.h[1].flat_b + row, s_bgrad[p.enc_cum[0] + row]);
       if (row == 3) atomicAdd(flat_grad + p.h[0].flat_b, s_bgrad[p.enc_cum[0] + 3]);
@@ -729,12 +731,6 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
             *reinterpret_cast<uint4*>(sInd + tile_piece(row, 0, 16)) = make_uint4(w[0], w[1], w[2], w[3]);
             *reinterpret_cast<uint4*>(sInd + tile_piece(row, 1, 16)) = make_uint4(w[4], w[5], w[6], w[7]);
           } else {
-            // d_raw of this point as a 16-column operand tile (columns 0..3 live): B operand of the heads' jobs
-            uint32_t h01, l01, h23, l23;
-            split_f16x2(dr[0], dr[1], h01, l01);
-            split_f16x2(dr[2], dr[3], h23, l23);
-            *reinterpret_cast<uint4*>(sD + tile_piece(row, 0, 16)) = make_uint4(h01, h23, 0u, 0u);
-            *reinterpret_cast<uint4*>(sD + kIndBytes + tile_piece(row, 0, 16)) = make_uint4(l01, l23, 0u, 0u);
             if (p.use_viewdirs && row < n_rays_tile * 3) {
               const int jr = row / 3, c = row - 3 * jr;
               const float vv = rays[(first_ray + jr) * ray_stride + 8 + c];
@@ -811,6 +807,10 @@ int bwd_tc_supported(const Plan& p, int n_samples, const char* what) {
   if (rc) return rc;
   if (!p.use_viewdirs) {
     set_error("%s impl=1 (tcgen05): the fused backward needs a view-dependent model (fc_rgb / fc_alpha heads); use impl=0", what);
+    return NERFB200_ERR_UNSUPPORTED;
+  }
+  if (p.dim_dir > 28) {
+    set_error("%s impl=1 (tcgen05): direction encodings wider than 28 not supported by the fused backward; use impl=0", what);
     return NERFB200_ERR_UNSUPPORTED;
   }
   if (smem_map_b(p).n_stages < 2) {

@@ -358,41 +358,61 @@ mlp_fwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
         FPROF_MARK(_tm);
         FPROF_SCOPE(8, mbar_wait(bar_a + 8 * s, a_ph));
         tc_fence_after();
-        for (int ks0 = 0; ks0 < mi.ksteps; ks0 += kStepsPerStage) {
-          FPROF_SCOPE(9, mbar_wait(bar_full + 8 * pp.stage, pp.phase));
+        // Two ring stages (four k-steps, twelve MMAs) per batch: the hand-over between stages (commit, barrier wait,
+        // fence, election, descriptor arithmetic: ~100 cycles during which the tensor pipe runs dry -- measured 82
+        // cycles per MMA against 64 nominal with one stage per batch) is paid half as often.
+        for (int ks0 = 0; ks0 < mi.ksteps;) {
+          const uint32_t st0 = pp.stage;
+          FPROF_SCOPE(9, mbar_wait(bar_full + 8 * st0, pp.phase));
+          pp.advance(n_stages);
+          const bool two = ks0 + kStepsPerStage < mi.ksteps;
+          const uint32_t st1 = pp.stage;
+          if (two) {
+            FPROF_SCOPE(9, mbar_wait(bar_full + 8 * st1, pp.phase));
+            pp.advance(n_stages);
+          }
           tc_fence_after();
-          const uint64_t b_st = desc_adv(b_ring, pp.stage * (uint32_t)kStageBytes);
 #if defined(NERFB200_EXP) && NERFB200_EXP == 2   // timing experiment: no MMAs (results are garbage)
-          if (elect_one()) mma_commit(bar_empty + 8 * pp.stage);
+          if (elect_one()) {
+            mma_commit(bar_empty + 8 * st0);
+            if (two) mma_commit(bar_empty + 8 * st1);
+          }
           if (false) {
 #else
           if (elect_one()) {
 #endif
 #pragma unroll
-            for (int hh = 0; hh < kStepsPerStage; ++hh) {
-              const int ks = ks0 + hh;
-              if (ks < mi.ksteps) {
-                const uint64_t b_hs = desc_adv(b_st, hh * 6 * slab_b);
-                const uint64_t b_h = desc_adv(b_hs, 2 * slab_b);
-                const uint64_t b_l = desc_adv(b_hs, 4 * slab_b);
-                const uint32_t acc0 = ks > 0 ? 1u : 0u;
-                if (ks < mi.ksteps_h) {
-                  mma_ts_f16(t_acc, t_ahi + 8 * ks, b_hs, idesc, acc0);
-                  mma_ts_f16(t_acc, t_alo + 8 * ks, b_h, idesc, 1u);
-                  mma_ts_f16(t_acc, t_ahi + 8 * ks, b_l, idesc, 1u);
-                } else {  // encodings: K-major view of the operand tile (SBO = next 8 points, LBO = next 8 features)
-                  const uint32_t off = (uint32_t)(ks - mi.ksteps_h) * 256u;
-                  const uint64_t e_hi_d = desc_adv(e_hi_d0, off), e_lo_d = desc_adv(e_lo_d0, off);
-                  mma_ss_f16(t_acc, e_hi_d, b_hs, idesc, acc0);
-                  mma_ss_f16(t_acc, e_lo_d, b_h, idesc, 1u);
-                  mma_ss_f16(t_acc, e_hi_d, b_l, idesc, 1u);
+            for (int half_b = 0; half_b < 2; ++half_b) {
+              if (half_b == 0 || two) {
+                const uint32_t st = half_b ? st1 : st0;
+                const uint64_t b_st = desc_adv(b_ring, st * (uint32_t)kStageBytes);
+#pragma unroll
+                for (int hh = 0; hh < kStepsPerStage; ++hh) {
+                  const int ks = ks0 + half_b * kStepsPerStage + hh;
+                  if (ks < mi.ksteps) {
+                    const uint64_t b_hs = desc_adv(b_st, hh * 6 * slab_b);
+                    const uint64_t b_h = desc_adv(b_hs, 2 * slab_b);
+                    const uint64_t b_l = desc_adv(b_hs, 4 * slab_b);
+                    const uint32_t acc0 = ks > 0 ? 1u : 0u;
+                    if (ks < mi.ksteps_h) {
+                      mma_ts_f16(t_acc, t_ahi + 8 * ks, b_hs, idesc, acc0);
+                      mma_ts_f16(t_acc, t_alo + 8 * ks, b_h, idesc, 1u);
+                      mma_ts_f16(t_acc, t_ahi + 8 * ks, b_l, idesc, 1u);
+                    } else {  // encodings: K-major view of the operand tile (SBO = next 8 points, LBO = next 8 features)
+                      const uint32_t off = (uint32_t)(ks - mi.ksteps_h) * 256u;
+                      const uint64_t e_hi_d = desc_adv(e_hi_d0, off), e_lo_d = desc_adv(e_lo_d0, off);
+                      mma_ss_f16(t_acc, e_hi_d, b_hs, idesc, acc0);
+                      mma_ss_f16(t_acc, e_lo_d, b_h, idesc, 1u);
+                      mma_ss_f16(t_acc, e_hi_d, b_l, idesc, 1u);
+                    }
+                  }
                 }
+                mma_commit(bar_empty + 8 * st);  // frees the ring stage once these MMAs have read it
               }
             }
-            mma_commit(bar_empty + 8 * pp.stage);  // frees the ring stage once these MMAs have read it
           }
           __syncwarp();
-          pp.advance(n_stages);
+          ks0 += (two ? 2 : 1) * kStepsPerStage;
         }
         a_ph ^= 1;
         if (elect_one()) mma_commit(bar_acc + 8 * s);  // accumulator of this MMA complete

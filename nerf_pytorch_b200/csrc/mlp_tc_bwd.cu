@@ -319,20 +319,29 @@ mlp_bwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
           const uint32_t idesc = make_idesc_f16(g.k_h);
           const uint32_t slab_b = 16u * (uint32_t)g.k_h;
           const uint64_t b_ring = make_desc(smem_u32(sm + mp.ring), slab_b, 128);
-          for (int ks = 0; ks < (g.n >> 4); ++ks) {
-            PROF_SCOPE(9, mbar_wait(&w_full[pp.stage], pp.phase));
+          // two ring stages (k-steps) per batch: six MMAs back to back, the stage hand-over is paid half as often
+          for (int ks = 0; ks < (g.n >> 4); ks += 2) {
+            const uint32_t st0 = pp.stage;
+            PROF_SCOPE(9, mbar_wait(&w_full[st0], pp.phase));
+            pp.advance(n_stages);
+            const uint32_t st1 = pp.stage;
+            PROF_SCOPE(9, mbar_wait(&w_full[st1], pp.phase));   // g.n is a multiple of 32: k-steps come in pairs
+            pp.advance(n_stages);
             tc_fence_after();
             if (elect_one()) {
-              const uint64_t b_hs = desc_adv(b_ring, pp.stage * (uint32_t)kWStage);
-              const uint64_t b_h = desc_adv(b_hs, 2 * slab_b);
-              const uint64_t b_l = desc_adv(b_hs, 4 * slab_b);
-              mma_ts_f16(t_acc, t_ahi + 8 * ks, b_hs, idesc, ks > 0 ? 1u : 0u);
-              mma_ts_f16(t_acc, t_alo + 8 * ks, b_h, idesc, 1u);
-              mma_ts_f16(t_acc, t_ahi + 8 * ks, b_l, idesc, 1u);
-              mma_commit(&w_empty[pp.stage]);
+#pragma unroll
+              for (int hb = 0; hb < 2; ++hb) {
+                const uint32_t st = hb ? st1 : st0;
+                const uint64_t b_hs = desc_adv(b_ring, st * (uint32_t)kWStage);
+                const uint64_t b_h = desc_adv(b_hs, 2 * slab_b);
+                const uint64_t b_l = desc_adv(b_hs, 4 * slab_b);
+                mma_ts_f16(t_acc, t_ahi + 8 * (ks + hb), b_hs, idesc, (ks + hb) > 0 ? 1u : 0u);
+                mma_ts_f16(t_acc, t_alo + 8 * (ks + hb), b_h, idesc, 1u);
+                mma_ts_f16(t_acc, t_ahi + 8 * (ks + hb), b_l, idesc, 1u);
+                mma_commit(&w_empty[st]);
+              }
             }
             __syncwarp();
-            pp.advance(n_stages);
           }
           if (elect_one()) mma_commit(bar_acc);
           __syncwarp();

@@ -4,7 +4,7 @@ import collections, csv, json, os, subprocess, sys
 
 tag, launches, rep = sys.argv[1:4]
 out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles")
-rows = list(csv.reader(open(launches)))
+rows = list(csv.reader(l for l in open(launches) if l.startswith('"')))
 hi = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
 hdr = rows[hi]
 ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
@@ -50,14 +50,15 @@ def gb(x):
     v, u = x.split()
     return float(v) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[u]
 # bench.py's roofline traffic figures: DRAM bytes of the FIRST captured launch of the forward chain kernel
-# (inference-mode fine pass) and of the wgrad kernel.  argv[4] = architecture tag (A0 | A1)
+# (inference-mode fine pass), of the training forward and of the fused backward.  argv[4] = architecture tag (A0 | A1)
 if len(sys.argv) > 4:
-    path = os.path.join(out_dir, "r1_ncu_summary.json")
+    path = os.path.join(out_dir, "r2_ncu_summary.json")
     cur = json.load(open(path)) if os.path.exists(path) else {}
-    for needle, key in (("mlp_chain_tc_kernel<0>", f"mlp_fwd_tc_{sys.argv[4]}_dram_bytes"),
-                        ("mlp_wgrad_tc_kernel", f"mlp_wgrad_tc_{sys.argv[4]}_dram_bytes")):
+    for needle, key in (("mlp_fwd_tc_kernel<0>", f"mlp_fwd_tc_{sys.argv[4]}_dram_bytes"),
+                        ("mlp_fwd_tc_kernel<1>", f"mlp_fwd_train_tc_{sys.argv[4]}_dram_bytes"),
+                        ("mlp_bwd_tc_kernel", f"mlp_bwd_tc_{sys.argv[4]}_dram_bytes")):
         for d in summ:
-            if needle in d.get("Kernel Name", ""):
+            if needle in d.get("Kernel Name", "").replace("(bool)", ""):
                 cur[key] = gb(d["dram__bytes_read.sum"]) + gb(d["dram__bytes_write.sum"])
                 break
     json.dump(cur, open(path, "w"), indent=1)

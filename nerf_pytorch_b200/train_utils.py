@@ -50,14 +50,30 @@ def set_default_impl(impl):
 # --------------------------------------------------------------------------------------------------
 # model / encoder introspection
 # --------------------------------------------------------------------------------------------------
+_PROBED: dict = {}   # id(callable) -> (weakref or None, result): an opaque encoder is probed once, not on every chunk
+
+
 def _probe_encoder(fn, dim_expected: Optional[int]):
     """(L, include_input, log_sampling) of an encoder.  ``Embedder`` objects carry their parameters;
     an opaque callable (the reference's own lambda, nerf_helpers.py:160-167) is identified by
-    evaluating it once on a CPU probe and matching the stock encoding."""
+    evaluating it once on a CPU probe and matching the stock encoding (memoised per callable)."""
     if fn is None:
         return None
     if isinstance(fn, Embedder) or all(hasattr(fn, a) for a in ("num_encoding_functions", "include_input", "log_sampling")):
         return int(fn.num_encoding_functions), bool(fn.include_input), bool(fn.log_sampling)
+    hit = _PROBED.get(id(fn))
+    if hit is not None and (hit[0] is None or hit[0]() is fn):
+        return hit[1]
+    res = _probe_encoder_uncached(fn)
+    try:
+        ref = weakref.ref(fn)
+    except TypeError:   # not weak-referenceable: keep it alive through the key's lifetime instead
+        ref = (lambda f: (lambda: f))(fn)
+    _PROBED[id(fn)] = (ref, res)
+    return res
+
+
+def _probe_encoder_uncached(fn):
     probe = torch.tensor([[0.3, -0.7, 1.1]], dtype=torch.float32)
     try:
         got = fn(probe)
@@ -152,6 +168,15 @@ def _flat_view_if_contiguous(params):
     if flat is not None and flat.data_ptr() == base and flat.numel() == off:
         return flat
     return None
+
+
+def invalidate(model) -> None:
+    """Drop the cached kernel blob of ``model``.  The cache key follows torch's parameter version counters and data
+    pointers, so every update made through torch ops (optimizers, ``copy_``, ``load_state_dict``) and through
+    ``FusedAdam`` is seen; call this after writing parameter memory behind torch's back (raw pointers, external kernels,
+    ``p.data`` views mutated by foreign code)."""
+    model._nerfb200_epoch = getattr(model, "_nerfb200_epoch", 0) + 1
+    _CACHE.pop(model, None)
 
 
 def _packed(model, arch: ops.ArchSpec):

@@ -80,6 +80,28 @@ def test_encoder_probe_identifies_reference_lambdas():
         train_utils._probe_encoder(lambda x: torch.tanh(x), None)
 
 
+def test_encoder_probe_is_memoised_and_invalidate_bumps_the_cache_epoch():
+    import nerf_pytorch_b200 as nb
+    from nerf_pytorch_b200 import train_utils
+    from oracle import nerf_oracle as O
+
+    calls = []
+
+    def enc(x):
+        calls.append(1)
+        return O.positional_encoding(x, 10, True, True)
+
+    assert train_utils._probe_encoder(enc, None) == (10, True, True)
+    n = len(calls)
+    for _ in range(5):   # every chunk of every iteration asks again: no further evaluations of the user's callable
+        assert train_utils._probe_encoder(enc, None) == (10, True, True)
+    assert len(calls) == n
+    m = nb.FlexibleNeRFModel()
+    e0 = getattr(m, "_nerfb200_epoch", 0)
+    nb.invalidate(m)
+    assert m._nerfb200_epoch == e0 + 1 and m not in train_utils._CACHE
+
+
 def test_model_introspection_and_state_dict_compat():
     import nerf_pytorch_b200 as nb
     from nerf_pytorch_b200 import train_utils

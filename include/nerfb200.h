@@ -69,7 +69,9 @@ int64_t nerfb200_launch_count(void);
  * weight-gradient job, the ReLU bit masks and d_raw -- the algorithmic traffic of its roofline */
 int64_t nerfb200_bwd_bytes_per_point(const nerfb200_arch_t* arch);
 /* NERFB200_OK if `impl` (0 fp32 CUDA cores, 1 tcgen05) can run this architecture forward AND backward with
- * n_samples samples per ray, else NERFB200_ERR_UNSUPPORTED (reason in nerfb200_last_error()) */
+ * n_samples samples per ray, else NERFB200_ERR_UNSUPPORTED (reason in nerfb200_last_error()).  impl = 2 asks for the
+ * tcgen05 FORWARD alone (inference: training = 0 in render_fwd / stash = NULL in mlp_fwd with impl = 1), which also
+ * covers hidden_size 256 */
 int32_t nerfb200_impl_supported(const nerfb200_arch_t* arch, int32_t n_samples, int32_t impl);
 
 /* ---- parameters -------------------------------------------------------------------------------

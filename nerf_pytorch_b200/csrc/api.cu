@@ -275,6 +275,7 @@ int32_t nerfb200_impl_supported(const nerfb200_arch_t* arch, int32_t n_samples, 
   NB_TRY(build_plan(arch, &p));
   if (impl == 0) return NERFB200_OK;
   if (impl == 1) return bwd_tc_supported(p, n_samples, "impl_supported");
+  if (impl == 2) return tc_supported(p, n_samples, "impl_supported", /*training=*/false);  // tcgen05 forward only (inference)
   set_error("unknown impl %d", impl);
   return NERFB200_ERR_INVALID;
 }

@@ -102,7 +102,7 @@ int launch_mlp_wgrad(const Plan& p, const float* rays, int ray_stride, const flo
 int launch_mlp_bwd_tc(const Plan& p, const float* blob, const float* rays, int ray_stride, int64_t n_rays, int n_samples,
                       const float* d_raw, const float* stash, float* scratch, float* flat_grad, cudaStream_t s);
 int64_t bwd_tc_scratch_floats(const Plan& p);
-int tc_supported(const Plan& p, int n_samples, const char* what);      // forward
+int tc_supported(const Plan& p, int n_samples, const char* what, bool training);  // forward (training: + stash)
 int bwd_tc_supported(const Plan& p, int n_samples, const char* what);  // forward + backward
 int launch_composite_fwd(const float* raw, const float* z, const float* rays, int ray_stride, const float* noise,
                          int64_t n_rays, int n_samples, float noise_std, int white_bkgd, float* out,

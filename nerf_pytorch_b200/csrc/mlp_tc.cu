@@ -44,8 +44,10 @@ constexpr int kStageBytes = kStepsPerStage * 96 * 128;  // 24 KB: 3 copies x 2 s
 constexpr int kMaxStages = 6;
 constexpr int kEncBytes = 32768;                     // per slot: encoding operand tile, hi block then lo block (<= 64 wide)
 constexpr int kMaxRaysPerTile = 10;
-constexpr uint32_t kTmemCols = 512, kSlotCols = 256;
-constexpr uint32_t kColAcc = 0, kColAhi = 128, kColAlo = 192;
+constexpr uint32_t kTmemCols = 512;
+// Tensor-memory columns of one slot: [0, H) accumulator, [H, 3H/2) A_hi, [3H/2, 2H) A_lo (two fp16 per column).
+// hidden 128: two slots of 256 columns; hidden 256 (inference only): ONE slot fills all 512 columns.
+__host__ __device__ inline int n_slots(const Plan& p) { return p.hidden == 128 ? 2 : 1; }
 constexpr int kSmemLimit = 232448 - 1024;            // 227 KB minus the alignment slack
 
 // Shared memory map (bytes from the 1 KB-aligned base), computed identically on host and device.
@@ -57,11 +59,11 @@ __host__ __device__ inline SmemMap smem_map(const Plan& p) {
   m.enc = 0;                                        // 2 slots x 32 KB: encodings as fp16 operand tiles (hi | lo)
   int off = m.enc + 2 * kEncBytes;
   m.bias = off;      off += p.enc_cum[0] * 4;       // sum of n over the gemm layers (bias * 2048 / 16)
-  m.headw = off;     off += (4 * 128 + 3 * 64 + 16) * 4;
-  m.viewb = off;     off += 2 * kMaxRaysPerTile * 64 * 4;
+  m.headw = off;     off += (4 * p.hidden + 3 * (p.hidden / 2) + 16) * 4;
+  m.viewb = off;     off += 2 * kMaxRaysPerTile * (p.hidden / 2) * 4;
   m.encd = off;      off += 2 * kMaxRaysPerTile * 32 * 4;
   m.hpart = off;     off += 2 * 2 * 128 * 4 * 4;    // [slot][head][row][4]
-  m.wv = off;        off += 32 * 64 * 4;            // direction-encoding rows of layers_dir[0]'s weight: Wt[k_h + k][n]
+  m.wv = off;        off += 32 * (p.hidden / 2) * 4;  // direction-encoding rows of layers_dir[0]'s weight: Wt[k_h + k][n]
   m.bars = off;      off += 256;
   off = (off + 1023) & ~1023;
   m.ring = off;
@@ -88,10 +90,10 @@ struct Cursor {
 struct Seq {
   int E, half_ticks;
   Cursor c0, c1;
-  __device__ __forceinline__ Seq(int events, int my_tiles) {
+  __device__ __forceinline__ Seq(int events, int my_tiles, int slots) {
     E = events;
     const int off1 = events >> 1;
-    const int n0 = (my_tiles + 1) >> 1, n1 = my_tiles >> 1;
+    const int n0 = slots == 2 ? (my_tiles + 1) >> 1 : my_tiles, n1 = slots == 2 ? my_tiles >> 1 : 0;
     const int t0 = n0 * E, t1 = n1 > 0 ? off1 + n1 * E : 0;
     half_ticks = 2 * (t0 > t1 ? t0 : t1);
     c0.idx = 0; c0.j = 0; c0.e = 0; c0.n = n0;
@@ -107,6 +109,7 @@ struct MmaInfo {
   uint32_t kbytes;      // bytes of one k-step
   int ksteps, ksteps_h; // k-steps, of which the first ksteps_h read A from tensor memory (the rest: encodings)
   int n_mma;            // N of the instruction
+  int sps;              // k-steps per ring stage (a stage holds 24 KB: two k-steps at N <= 128, one at N = 256)
 };
 __device__ __forceinline__ MmaInfo mma_info(const Plan& p, const float* blob, int e) {
   MmaInfo mi;
@@ -116,6 +119,7 @@ __device__ __forceinline__ MmaInfo mma_info(const Plan& p, const float* blob, in
   mi.ksteps = (g.k_tc + 15) >> 4;
   mi.ksteps_h = g.k_h >> 4;
   mi.kbytes = 96u * (uint32_t)mi.n_mma;
+  mi.sps = mi.n_mma > 128 ? 1 : kStepsPerStage;   // (always kStepsPerStage in the hidden-128 instantiations)
   return mi;
 }
 
@@ -236,7 +240,8 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], int c0, 
 }
 
 // kTrain: the forward also writes the activation stash (operand tiles + ReLU bit masks + the encoding tile).
-template <bool kTrain>
+// kH = hidden size (compile-time: the tensor-memory column map and the slot count fold into constants)
+template <bool kTrain, int kH>
 __global__ void __launch_bounds__(kThreadsTc, 1)
 mlp_fwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob, const float* __restrict__ rays,
                   int ray_stride, const float* __restrict__ z, int64_t P, int S, int64_t n_tiles,
@@ -313,7 +318,10 @@ mlp_fwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
   const int my_tiles = (n_tiles > blockIdx.x) ? (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
   const int E = p.n_gemm + 1;
   const int nM = E - 1;
-  const Seq seq(E, my_tiles);
+  constexpr int slots = kH == 128 ? 2 : 1;
+  const Seq seq(E, my_tiles, slots);
+  constexpr uint32_t kSlotCols = 2u * kH, kColAcc = 0u, kColAhi = kH, kColAlo = kH + kH / 2;
+  constexpr int vbs = kH / 2;   // row stride of the per-ray bias table (= width of layers_dir[0])
   const uint32_t ring_a = smem_u32(sm + mp.ring);
 
   if (warp == kProdWarp) {
@@ -325,8 +333,9 @@ mlp_fwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
       for (int h = 0; h < seq.half_ticks; ++h) {
         if (cur.active() && cur.e < nM) {
           const MmaInfo mi = mma_info(p, blob, cur.e);
-          for (int ks = 0; ks < mi.ksteps; ks += kStepsPerStage) {
-            const uint32_t bytes = (uint32_t)min(kStepsPerStage, mi.ksteps - ks) * mi.kbytes;
+          const int sps = kH == 128 ? kStepsPerStage : mi.sps;
+          for (int ks = 0; ks < mi.ksteps; ks += sps) {
+            const uint32_t bytes = (uint32_t)min(sps, mi.ksteps - ks) * mi.kbytes;
             FPROF_SCOPE(11, mbar_wait(bar_empty + 8 * pp.stage, pp.phase ^ 1));
             mbar_arrive_expect_tx(bar_full + 8 * pp.stage, bytes);
             bulk_g2s_hint(ring_a + pp.stage * kStageBytes, mi.src + (size_t)ks * mi.kbytes, bytes,
@@ -347,6 +356,7 @@ mlp_fwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
       if (cur.active() && cur.e < nM) {
         const uint32_t s = (uint32_t)(h & 1);
         const MmaInfo mi = mma_info(p, blob, cur.e);
+        const int sps = kH == 128 ? kStepsPerStage : mi.sps;
         const uint32_t idesc = make_idesc_f16(mi.n_mma);
         const uint32_t slab_b = 16u * (uint32_t)mi.n_mma;  // bytes of one weight slab
         const uint32_t t_acc = tmem + s * kSlotCols + kColAcc;
@@ -365,7 +375,7 @@ mlp_fwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
           const uint32_t st0 = pp.stage;
           FPROF_SCOPE(9, mbar_wait(bar_full + 8 * st0, pp.phase));
           pp.advance(n_stages);
-          const bool two = ks0 + kStepsPerStage < mi.ksteps;
+          const bool two = ks0 + sps < mi.ksteps;
           const uint32_t st1 = pp.stage;
           if (two) {
             FPROF_SCOPE(9, mbar_wait(bar_full + 8 * st1, pp.phase));
@@ -388,8 +398,8 @@ mlp_fwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
                 const uint64_t b_st = desc_adv(b_ring, st * (uint32_t)kStageBytes);
 #pragma unroll
                 for (int hh = 0; hh < kStepsPerStage; ++hh) {
-                  const int ks = ks0 + half_b * kStepsPerStage + hh;
-                  if (ks < mi.ksteps) {
+                  const int ks = ks0 + half_b * sps + hh;
+                  if (hh < sps && ks < mi.ksteps) {
                     const uint64_t b_hs = desc_adv(b_st, hh * 6 * slab_b);
                     const uint64_t b_h = desc_adv(b_hs, 2 * slab_b);
                     const uint64_t b_l = desc_adv(b_hs, 4 * slab_b);
@@ -412,7 +422,7 @@ mlp_fwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
             }
           }
           __syncwarp();
-          ks0 += (two ? 2 : 1) * kStepsPerStage;
+          ks0 += (two ? 2 : 1) * sps;
         }
         a_ph ^= 1;
         if (elect_one()) mma_commit(bar_acc + 8 * s);  // accumulator of this MMA complete
@@ -440,7 +450,7 @@ mlp_fwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
       const uint32_t t_ahi = tmem + lane_base + s * kSlotCols + kColAhi;
       const uint32_t t_alo = tmem + lane_base + s * kSlotCols + kColAlo;
       uint8_t* e_hi = sm + mp.enc + s * kEncBytes;
-      float* viewb = s_viewb + s * kMaxRaysPerTile * 64;
+      float* viewb = s_viewb + s * kMaxRaysPerTile * vbs;
       float* encd = s_encd + s * kMaxRaysPerTile * 32;
       float* hpart = s_hpart + s * 2 * 128 * 4;
 
@@ -448,7 +458,7 @@ mlp_fwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
       if (e == 0) {
         // ================= new tile: encodings of this row -> operand tile (value / 16), the two halves split the
         // frequencies
-        ts.tile = blockIdx.x + (int64_t)(2 * j + s) * gridDim.x;
+        ts.tile = blockIdx.x + (int64_t)(slots * j + s) * gridDim.x;
         ts.p0 = ts.tile * kTileRows;
         ts.pt = ts.p0 + row;
         ts.valid = ts.pt < P;
@@ -503,7 +513,7 @@ mlp_fwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
             const int jr = i / gd.n, n = i - jr * gd.n;
             float a = 0.f;
             for (int k = 0; k < p.dim_dir; ++k) a = fmaf(encd[jr * 32 + k], s_wv[k * gd.n + n], a);
-            viewb[jr * 64 + n] = fmaf(a, kActScale * kLoScale, s_bias[gd.cum_n + n]);  // per-ray bias of layers_dir[0] (x 2048 / 16)
+            viewb[jr * vbs + n] = fmaf(a, kActScale * kLoScale, s_bias[gd.cum_n + n]);  // per-ray bias of layers_dir[0] (x 2048 / 16)
           }
         }
         tc_fence_before();
@@ -542,7 +552,7 @@ mlp_fwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
 
       {
         ChunkArgs ca;
-        ca.bias = is_dir ? viewb + ts.ray_slot * 64 : s_bias + g.cum_n;
+        ca.bias = is_dir ? viewb + ts.ray_slot * vbs : s_bias + g.cum_n;
         ca.lb = g.relu ? 0.f : -3.4e38f;
         ca.hw = hw; ca.hk = hk; ca.hn = hn;
         ca.has_next = has_next;
@@ -553,7 +563,7 @@ mlp_fwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
                         tile_piece(row, 0, g.n);
         // column chunks of this thread: [32*half, +32) and, for 128-wide layers, [64 + 32*half, +32), one after the
         // other (112 registers per thread: one 32-column chunk at a time)
-        const int nch = g.n >> 6;  // 2 for 128-wide layers, 1 for 64-wide ones
+        const int nch = g.n >> 6;  // 64-column pairs of chunks: 4 / 2 / 1 for 256 / 128 / 64-wide layers
 #pragma unroll 1
         for (int ch = 0; ch < nch; ++ch) {
           const int c0 = 64 * ch + 32 * half;
@@ -611,9 +621,12 @@ mlp_fwd_tc_kernel(const __grid_constant__ Plan p, const float* __restrict__ blob
   if (warp == kMmaWarp) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols));
 }
 
-int tc_supported(const Plan& p, int n_samples, const char* what) {
-  if (p.hidden != 128) {
-    set_error("%s impl=1 (tcgen05): hidden_size %d not supported (128 only); use impl=0", what, p.hidden);
+// training = the forward must also write the activation stash for the fused backward (hidden 128 only); the
+// inference forward also runs hidden 256 (one tile in flight per CTA, N = 256 MMAs)
+int tc_supported(const Plan& p, int n_samples, const char* what, bool training) {
+  if (p.hidden != 128 && (training || p.hidden != 256)) {
+    set_error("%s impl=1 (tcgen05): hidden_size %d not supported (training: 128 only; inference: 128 or 256); use impl=0", what,
+              p.hidden);
     return NERFB200_ERR_UNSUPPORTED;
   }
   if (p.dim_xyz_pad > 64 || p.dim_dir > 32) {
@@ -632,18 +645,18 @@ int tc_supported(const Plan& p, int n_samples, const char* what) {
   return NERFB200_OK;
 }
 
-template <bool kTrain>
+template <bool kTrain, int kH>
 static int launch_fwd(const Plan& p, const float* blob, const float* rays, int ray_stride, const float* z, int64_t P,
                       int n_samples, float* raw, float* stash, cudaStream_t s, const char* what) {
   const int64_t tiles = (P + kTileRows - 1) / kTileRows;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  // two tiles in flight per CTA: do not spread fewer than 2 tiles per CTA over more CTAs than needed
-  int64_t want = (tiles + 1) / 2;
+  // two tiles in flight per CTA (hidden 128): do not spread fewer than 2 tiles per CTA over more CTAs than needed
+  int64_t want = n_slots(p) == 2 ? (tiles + 1) / 2 : tiles;
   const int grid = (int)(want < sms ? (want < 1 ? 1 : want) : sms);
   const size_t bytes = (size_t)smem_map(p).total + 1024;
-  auto kern = mlp_fwd_tc_kernel<kTrain>;
+  auto kern = mlp_fwd_tc_kernel<kTrain, kH>;
   int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes), what);
   if (rc) return rc;
   kern<<<grid, kThreadsTc, bytes, s>>>(p, blob, rays, ray_stride, z, P, n_samples, tiles, raw, stash);
@@ -653,13 +666,16 @@ static int launch_fwd(const Plan& p, const float* blob, const float* rays, int r
 
 int launch_mlp_fwd_tc(const Plan& p, const float* blob, const float* rays, int ray_stride, const float* z,
                       int64_t n_rays, int n_samples, float* raw, float* stash, cudaStream_t s) {
-  int rc = tc_supported(p, n_samples, "mlp_fwd");
+  int rc = tc_supported(p, n_samples, "mlp_fwd", stash != nullptr);
   if (rc) return rc;
   if (stash)
-    return launch_fwd<true>(p, blob, rays, ray_stride, z, n_rays * n_samples, n_samples, raw, stash, s,
-                            "mlp_fwd_tc launch");
-  return launch_fwd<false>(p, blob, rays, ray_stride, z, n_rays * n_samples, n_samples, raw, nullptr, s,
-                           "mlp_fwd_tc launch");
+    return launch_fwd<true, 128>(p, blob, rays, ray_stride, z, n_rays * n_samples, n_samples, raw, stash, s,
+                                 "mlp_fwd_tc launch");
+  if (p.hidden == 256)
+    return launch_fwd<false, 256>(p, blob, rays, ray_stride, z, n_rays * n_samples, n_samples, raw, nullptr, s,
+                                  "mlp_fwd_tc launch");
+  return launch_fwd<false, 128>(p, blob, rays, ray_stride, z, n_rays * n_samples, n_samples, raw, nullptr, s,
+                                "mlp_fwd_tc launch");
 }
 
 }  // namespace nerfb200

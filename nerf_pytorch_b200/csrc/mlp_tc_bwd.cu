@@ -812,7 +812,7 @@ int64_t bwd_tc_scratch_floats(const Plan& p) {
 }
 
 int bwd_tc_supported(const Plan& p, int n_samples, const char* what) {
-  int rc = tc_supported(p, n_samples, what);
+  int rc = tc_supported(p, n_samples, what, /*training=*/true);
   if (rc) return rc;
   if (!p.use_viewdirs) {
     set_error("%s impl=1 (tcgen05): the fused backward needs a view-dependent model (fc_rgb / fc_alpha heads); use impl=0", what);

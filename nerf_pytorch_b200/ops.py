@@ -16,6 +16,7 @@ from ._lib import Arch, RenderOpts
 
 IMPL_SIMT = 0  # fp32 CUDA cores
 IMPL_TC = 1    # tcgen05 tensor cores (fp16x2 three-term splits, fp32 accumulation)
+IMPL_TC_FWD = 2  # query only (impl_supported): the tcgen05 forward alone (inference), which also runs hidden 256
 
 
 def _ptr(t: Optional[torch.Tensor]):

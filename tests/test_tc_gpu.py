@@ -129,6 +129,36 @@ def test_tc_forward_matches_simt_and_oracle(name):
             assert (a1 - a0).abs().max().item() <= 3e-5 * s + 1e-7, (tag, lname, (a1 - a0).abs().max().item(), s)
 
 
+@pytest.mark.parametrize("viewdirs", [True, False])
+def test_tc_forward_hidden_256_matches_oracle_and_fp32_kernel(viewdirs):
+    """pretrained/*/config.yml as written (8 x 256, skip 4): the tcgen05 inference forward (one tile in flight, N = 256 MMAs)
+    against the fp64 oracle MLP and the fp32 CUDA-core kernel, ragged tile tail included."""
+    from nerf_pytorch_b200 import ops
+    from oracle import nerf_oracle as O
+
+    arch = ops.ArchSpec(num_layers=8, hidden=256, skip_every=4, n_freq_xyz=10, n_freq_dir=4, use_viewdirs=viewdirs)
+    g = torch.Generator().manual_seed(3)
+    sd = O.init_flexible_nerf(8, 256, 4, 10, 4, use_viewdirs=viewdirs, generator=g)
+    n, s_ = 37, 52   # 1924 points: 15 full tiles + a ragged one, tiles straddle rays
+    d = torch.randn(n, 3, generator=g)
+    rays = torch.cat([torch.randn(n, 3, generator=g) * 0.3, d, torch.full((n, 1), 2.0), torch.full((n, 1), 6.0),
+                      d / d.norm(dim=-1, keepdim=True)], -1)
+    rays = (rays if viewdirs else rays[:, :8]).contiguous()
+    z = torch.sort(torch.rand(n, s_, generator=g) * 4 + 2, -1).values.contiguous()
+    blob = ops.pack_weights(arch, ops.flatten_state_dict(arch, sd, "cuda"))
+    raw0 = ops.mlp_fwd(arch, blob, rays.cuda(), z.cuda(), impl=ops.IMPL_SIMT)
+    raw1 = ops.mlp_fwd(arch, blob, rays.cuda(), z.cuda(), impl=ops.IMPL_TC)
+    torch.cuda.synchronize()
+    sd64 = {k: v.double() for k, v in sd.items()}
+    pts = (rays[:, None, :3] + rays[:, None, 3:6] * z[..., None]).double()
+    want = O.run_network(sd64, pts, rays.double(), 1 << 20, (10, True, True), (4, True, True) if viewdirs else None)
+    scale = want.abs().max().item()
+    e_tc = (raw1.cpu().double() - want).abs().max().item()
+    e_simt = (raw0.cpu().double() - want).abs().max().item()
+    assert e_tc <= 3e-5 * scale + 1e-6, (e_tc, e_simt, scale)
+    assert torch.isfinite(raw1).all()
+
+
 def test_tc_ragged_tail_and_sizes():
     """Tiles that straddle rays / a ragged last tile / 1 ray: same results as the fp32 kernel."""
     from nerf_pytorch_b200 import ops
@@ -275,9 +305,11 @@ def test_tc_unsupported_configs_are_refused():
     blob = ops.pack_weights(arch, torch.zeros(arch.flat_param_count(), device="cuda"))
     rays = torch.zeros(4, 11, device="cuda")
     z = torch.ones(4, 64, device="cuda")
-    with pytest.raises(NotImplementedError):
-        ops.mlp_fwd(arch, blob, rays, z, impl=ops.IMPL_TC)
+    with pytest.raises(NotImplementedError):   # hidden 256: no activation stash / fused backward on tcgen05 ...
+        ops.mlp_fwd(arch, blob, rays, z, impl=ops.IMPL_TC, want_stash=True)
+    ops.mlp_fwd(arch, blob, rays, z, impl=ops.IMPL_TC)   # ... but the inference forward runs
     assert not ops.impl_supported(arch, 64, ops.IMPL_TC)
+    assert ops.impl_supported(arch, 64, ops.IMPL_TC_FWD)
     assert ops.impl_supported(arch, 64, ops.IMPL_SIMT)
     # the fused backward rides the heads' weight gradients on layers_dir[0]: no view directions -> CUDA cores
     assert not ops.impl_supported(ops.ArchSpec(use_viewdirs=False), 64, ops.IMPL_TC)

@@ -1,6 +1,6 @@
 // mlp_tc.cu -- tcgen05 (5th-generation tensor core) implementation of the layer-chained forward kernel
 //   points -> positional encoding -> FlexibleNeRFModel   (nerf/train_utils.py:67, :8-25; nerf/models.py:233-256)
-// (the backward lives in mlp_tc_bwd.cu) for hidden_size 128, fp32-faithful through a 3-term split of every product
+// (the backward lives in mlp_tc_bwd.cu) for hidden_size 128 (and 256 in inference), fp32-faithful through a 3-term split of every product
 //     a * w  ~=  a_hi*w_hi + a_lo*w_hi + a_hi*w_lo          
 // on tcgen05.mma.kind::f16 (K = 16 per instruction): both operands are fp16 pairs (hi = fp16(x), lo = fp16((x - hi) 2^11),
 // 22 significant bits, tc_common.cuh split_f16x2); the weights come in three pre-scaled copies (hs | h | l, split_w3) so
@@ -8,24 +8,30 @@
 // The A operand holds activation / 16 (fp16 range 65504 -> 1.05e6: the shipped lego checkpoints reach 6e4);
 // conversions do not saturate, an out-of-range value turns the output into inf / NaN instead of clamping.
 //
-// Persistent kernels, one CTA per SM, 320 threads, TWO 128-point tiles in flight per CTA ("slots"): while the
-// epilogue warps work on one slot's accumulator, the tensor pipe runs the other slot's layer.
-//   warps 0-7  prologue/epilogue: thread (row = tid % 128, half = tid / 128) owns half of the columns of row
-//              `row` of a tile (= TMEM lane row).  Per layer: tcgen05.ld the fp32 accumulator, one FFMA for scale +
-//              bias, ReLU, narrow heads as register dot products, split into fp16 hi + lo and tcgen05.st back into
-//              tensor memory as the NEXT layer's A operand.  Training: the SAME hi / lo registers are also stored
-//              to the activation stash as an operand tile (tc_common.cuh "Operand tiles": eight lanes write one
-//              full 128-byte line), plus one ReLU bit per activation; no staging buffer, no extra barrier.
-//   warp 8     MMA issuer: one elected lane, tcgen05.mma.kind::f16 M=128, N=128|64, K=16, three per k-step;
-//              A from tensor memory (hidden activations / gradients) or shared memory (encodings), B = the three
-//              weight copies from the shared-memory ring (two k-steps = 24 KB per stage).
-//   warp 9     weight producer: one cp.async.bulk per stage from the L2-resident blob, mbarrier complete_tx
+// Persistent kernel, one CTA per SM, 576 threads, TWO 128-point tiles in flight per CTA ("slots") for hidden 128, each
+// with its OWN eight epilogue warps: the two slots' epilogues overlap on the four schedulers and each slot's MMAs run
+// under the other slot's epilogue.  (Hidden 256, inference only: ONE slot takes all of tensor memory; kH template.)
+//   warps 0-7 / 8-15  prologue/epilogue of slot 0 / 1: thread (row = gtid % 128, half = gtid / 128) owns half of the
+//              columns of row `row` of a tile (= TMEM lane row).  Per layer and 32-column chunk: tcgen05.ld the fp32
+//              accumulator, add the bias at the accumulator's 2^11 scale, NaN-propagating max (ReLU), narrow heads as
+//              register dot products, split into fp16 hi + lo (mixed-precision FMA, tc_common.cuh split_f16x2_y) and
+//              tcgen05.st back into tensor memory as the NEXT layer's A operand: 5 instructions per element.
+//              Training: the SAME hi / lo registers are also stored to the activation stash as an operand tile
+//              (tc_common.cuh "Operand tiles": eight lanes write one full 128-byte line), plus one ReLU bit per
+//              activation; no staging buffer, no extra barrier.  ONE instance of this code per kernel (55 KB of
+//              SASS; an earlier version with the chunk code inlined eight times spent 10 % of its issue slots on
+//              instruction fetch).
+//   warp 16    MMA issuer: one elected lane, tcgen05.mma.kind::f16 M=128, N=256|128|64, K=16, three per k-step, two
+//              ring stages (twelve MMAs) per batch; A from tensor memory (hidden activations) or shared memory
+//              (encodings), B = the three weight copies from the shared-memory ring (24 KB per stage).
+//   warp 17    weight producer: one cp.async.bulk per stage from the L2-resident blob, mbarrier complete_tx
 //              (measured: 113-123 B/cycle/SM of L2 -> shared bulk copies with all SMs streaming, profiles/r2_microbench*).
-// All three roles walk the same fixed sequence of events (tick, slot): slot 1 lags slot 0 by half a tile so that one
-// slot's prologue / last layer falls under the other slot's mid-chain layers.
-// Tensor memory (512 columns), per slot s at 256 s: [0,128) accumulator, [128,192) A_hi, [192,256) A_lo (two fp16
-// per column).  The direction encoding enters layers_dir[0] through a per-ray fp32 bias computed on the CUDA cores
-// (it is constant along a ray: SURVEY.md section 7.3 item 5), so that layer contracts over K = 128 only.
+// The MMA issuer and the producer walk a fixed interleaving of the two slots' layers (Seq / Cursor below); slot 1 lags
+// slot 0 by half a tile so that one slot's prologue / last layer falls under the other slot's mid-chain layers.
+// Tensor memory (512 columns), per slot s at 2 H s: [0,H) accumulator, [H,3H/2) A_hi, [3H/2,2H) A_lo (two fp16 per
+// column).  The direction encoding enters layers_dir[0] through a per-ray fp32 bias computed on the CUDA cores
+// (it is constant along a ray: SURVEY.md section 7.3 item 5), so that layer contracts over K = H only.
+// Measured (A1, 4096 x 192 points): 0.76 ms inference / 1.17 ms training, tensor pipe 46 % / 30 % (profiles/r2_final_*).
 #include "common.cuh"
 #include "tc_common.cuh"
 

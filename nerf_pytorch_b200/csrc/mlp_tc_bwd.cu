@@ -6,8 +6,8 @@
 //   wgrad  : dW_t[n][k] += sum_p G_t[p][n] X_{t-1}[p][k]                                    (M = features n, K = points)
 // Both are 3-term split-precision products on tcgen05.mma.kind::f16 (tc_common.cuh split_f16x2).  The trick that
 // makes the fusion cheap is the operand tile (tc_common.cuh "Operand tiles"): G_t is split into fp16 hi / lo ONCE in
-// the epilogue registers and stored ONCE to a shared-memory tile: its K-major view is the A operand of the chain MMA,
-// its MN-major view the A operand of the weight-gradient MMAs; the forward stashed every
+// the epilogue registers; the registers go to tensor memory (A operand of the chain MMA) and ONCE to a shared-memory
+// tile whose MN-major view is the A operand of the weight-gradient MMAs; the forward stashed every
 // layer's activation X_t as the same kind of tile, so the B operand of the weight-gradient MMAs is a plain bulk copy
 // from HBM.  Nothing is transposed on the CUDA cores.
 //
@@ -19,21 +19,27 @@
 //
 // Persistent kernel, one CTA per SM, 512 threads (register file rebalanced between the roles with setmaxnreg):
 //   warps 0-7  epilogue (thread = (point row, column half)): per layer  part A: chain accumulator -> + head term, ReLU
-//              mask, split into hi / lo registers;  part B (once the previous layer's jobs have finished reading the
-//              G tile): registers -> shared-memory G tile.
-//   warp 8     MMA issuer: chain MMA of the layer (A = G tile, K-major view; B = weights from the ring), then the layer's
-//              weight-gradient jobs (A = G tile, B = activation tile, both MN-major from shared memory), the
-//              16-column ray-indicator job that yields the bias gradients and the per-ray sums of layers_dir[0], and
-//              the two narrow heads' jobs with the roles swapped (A = activation tile, B = a 16-column d_raw tile).
-//   warp 9     weight producer (cp.async.bulk ring, one k-step per stage)
+//              mask, split into hi / lo registers (mixed-precision FMA split at the accumulator's 2^11 scale) ->
+//              TENSOR memory as the chain's A operand (the chain MMA may start);  part B (once the previous layer's
+//              jobs have finished reading the G tile): the same registers -> shared-memory G tile (the jobs may start).
+//   warp 8     MMA issuer: chain MMA of the layer (A = this layer's G from tensor memory, B = weights from the ring:
+//              an SS MMA at N = 128 reads 8 KB of shared memory per 64 cycles, the whole port, so the chain must not
+//              take both operands from there), then the layer's weight-gradient jobs (A = G tile, B = activation tile,
+//              both MN-major from shared memory), the 16-column ray-indicator job that yields the bias gradients and
+//              the per-ray sums of layers_dir[0], and the two narrow heads' jobs with the roles swapped (A = activation
+//              tile, B = d_raw = feature rows 64..79 of the first layer's G tile).
+//   warp 9     weight producer (cp.async.bulk ring, one k-step per stage, two stages per MMA batch)
 //   warp 10    activation-tile producer (hi block / lo block of one job at a time)
-//   warps 12-15 drain (thread = accumulator row): the finished weight-gradient accumulators, up to two layers behind
-//              the issuer (they are double-buffered in tensor memory by layer parity): tcgen05.ld -> unscale ->
-//              swizzled staging chunk (4 x 8 KB, rotating) -> cp.reduce.async.bulk .add.f32 into the L2-resident
-//              gradient blob; indicator sums -> bias / direction-encoding accumulators; heads' rows -> atomics.
-// Tensor memory: [0,128) chain accumulator; two buffers of 144 columns at 128 and 272 (main job 128 + indicator sums
-// 16), used alternately by consecutive layers; [416,480) the second job of a layer (encoding part of a skip layer /
-// of layer1's neighbour, at most 64 wide); [480,496) / [496,512) the heads' jobs.
+//   warps 12-15 drain (thread = accumulator row): the finished weight-gradient accumulators of the layer (single-
+//              buffered: the next layer's jobs wait for acc_free): tcgen05.ld 32 columns -> unscale -> swizzled 16 KB
+//              staging chunk (two, alternating) -> cp.reduce.async.bulk .add.f32 into the L2-resident gradient blob;
+//              indicator sums -> bias accumulators (shared memory) and the direction-encoding part of
+//              dW(layers_dir[0]) (registers); heads' rows -> atomics.
+// Tensor memory: [0,128) chain accumulator; [128,192) / [192,256) chain A operand hi / lo; [256,400) main job 128 +
+// indicator sums 16; [400,464) the second job of a layer (encoding part of a skip layer / of layer1's neighbour, at
+// most 64 wide); [464,480) / [480,496) the heads' jobs.
+// Measured (A1, 4096 x 192 points): 2.2 ms, tensor pipe 33 %, 4.35 GB of DRAM traffic (profiles/r2_final_*); the MMA warp
+// is occupied for the whole layer (cycle counters: tools/bwd_prof.py on a -DNERFB200_PROF build).
 #include "common.cuh"
 #include "tc_common.cuh"
 

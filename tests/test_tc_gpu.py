@@ -159,6 +159,42 @@ def test_tc_forward_hidden_256_matches_oracle_and_fp32_kernel(viewdirs):
     assert torch.isfinite(raw1).all()
 
 
+def test_hidden_256_renders_on_tcgen05_in_inference_and_trains_on_fp32_kernels():
+    """The automatic implementation choice for the shipped-checkpoint architecture (8 x 256): torch.no_grad() renders go
+    through the tcgen05 forward and agree with the fp32 CUDA-core path; a training step silently uses the fp32 kernels."""
+    import nerf_pytorch_b200 as nb
+    from nerf_pytorch_b200 import ops, train_utils
+    from oracle import nerf_oracle as O
+
+    torch.manual_seed(0)
+    kw = dict(num_layers=8, hidden_size=256, skip_connect_every=4, num_encoding_fn_xyz=10, num_encoding_fn_dir=4)
+    mc, mf = nb.FlexibleNeRFModel(**kw).cuda(), nb.FlexibleNeRFModel(**kw).cuda()
+    epf, edf = nb.get_embedding_function(10), nb.get_embedding_function(4)
+    arch = train_utils._arch_of(mc, (10, True, True), (4, True, True))
+    assert train_utils._auto_impl(arch, arch, 64, 64, training=False) == ops.IMPL_TC
+    assert train_utils._auto_impl(arch, arch, 64, 64, training=True) == ops.IMPL_SIMT
+    n = 300
+    d = torch.randn(n, 3, device="cuda")
+    ro, rd = torch.randn(n, 3, device="cuda") * 0.2 + torch.tensor([0.0, 0.0, 4.0], device="cuda"), -d.abs() * 0.3 - torch.tensor([0, 0, 1.0], device="cuda")
+    det = O.make_options(num_coarse=64, num_fine=64, perturb=False, radiance_field_noise_std=0.0)
+    with torch.no_grad():
+        out_tc = nb.run_one_iter_of_nerf(100, 100, 120.0, mc, mf, ro, rd, det, mode="validation", encode_position_fn=epf,
+                                         encode_direction_fn=edf)
+        out_32 = nb.run_one_iter_of_nerf(100, 100, 120.0, mc, mf, ro, rd, det, mode="validation", encode_position_fn=epf,
+                                         encode_direction_fn=edf, impl=ops.IMPL_SIMT)
+    for i, (a, b) in enumerate(zip(out_tc, out_32)):   # rgb / disp / acc of both passes: same renders to fp32 round-off
+        if i % 3 != 1:                                   # (disp is NaN on an empty ray in the reference too: compared NaN-aware)
+            assert torch.isfinite(a).all()
+        a, b = torch.nan_to_num(a, nan=0.0, posinf=0.0, neginf=0.0), torch.nan_to_num(b, nan=0.0, posinf=0.0, neginf=0.0)
+        assert (a - b).abs().max().item() <= 2e-5 * max(1.0, b.abs().max().item()), (i, (a - b).abs().max().item())
+    # training: no tcgen05 backward for hidden 256 -> the fp32 kernels, chosen by the library, gradients arrive
+    tr = O.make_options(num_coarse=32, num_fine=32, perturb=True, radiance_field_noise_std=0.2)
+    out = nb.run_one_iter_of_nerf(100, 100, 120.0, mc, mf, ro[:64], rd[:64], tr, mode="train", encode_position_fn=epf,
+                                  encode_direction_fn=edf)
+    (out[0].sum() + out[3].sum()).backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in list(mc.parameters()) + list(mf.parameters()))
+
+
 def test_tc_ragged_tail_and_sizes():
     """Tiles that straddle rays / a ragged last tile / 1 ray: same results as the fp32 kernel."""
     from nerf_pytorch_b200 import ops

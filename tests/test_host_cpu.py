@@ -189,3 +189,46 @@ def test_fp16x2_split_precision_model():
     smax = scaled.abs().amax(dim=1)
     assert bool(((smax >= 1.0) & (smax < 2.0)).all())
     assert torch.equal(scaled * (e << 23).view(torch.float32)[:, None], d)
+
+
+def test_cached_dataset_pool_reads_the_reference_cache_format(tmp_path):
+    """cache_dataset.py:104-135 files (one torch.save dict per image) -> one resident pool; sample() = the reference's
+    two-stage draw (train_nerf.py:175-193): one image, n distinct rays of it, targets cut to rgb."""
+    import nerf_pytorch_b200 as nb
+
+    g = torch.Generator().manual_seed(0)
+    os.makedirs(tmp_path / "train"), os.makedirs(tmp_path / "val")
+    imgs = []
+    for i, (shape, tch) in enumerate((((2, 50, 3), 3), ((2, 6, 8, 3), 4))):   # sampled-ray and whole-image variants, rgb / rgba
+        rb = torch.randn(*shape, generator=g)
+        tgt = torch.rand(*shape[1:-1], tch, generator=g)
+        torch.save({"height": 6, "width": 8, "focal_length": 11.5, "ray_bundle": rb, "target": tgt}, tmp_path / "train" / f"{i:04d}.data")
+        imgs.append((rb, tgt))
+    torch.save({"height": 6, "width": 8, "focal_length": 11.5, "ray_origins": torch.randn(6, 8, 3), "ray_directions": torch.randn(6, 8, 3),
+                "target": torch.rand(6, 8, 4)}, tmp_path / "val" / "0007.data")
+    pool = nb.CachedRayPool.from_dir(str(tmp_path), device="cpu")
+    assert pool.num_images == 2 and len(pool) == 50 + 48
+    seen = set()
+    for _ in range(20):
+        h, w, f, ro, rd, tg = pool.sample(16, generator=g)
+        assert (h, w, f) == (6, 8, 11.5) and ro.shape == rd.shape == tg.shape == (16, 3)
+        # the 16 rows are distinct rows of ONE cached image, with that image's directions and rgb targets
+        hit = None
+        for k, (rb, tgt) in enumerate(imgs):
+            o_all, d_all, t_all = rb[0].reshape(-1, 3), rb[1].reshape(-1, 3), tgt[..., :3].reshape(-1, 3)
+            idx = [(o_all == r).all(-1).nonzero() for r in ro]
+            if all(len(j) == 1 for j in idx):
+                j = torch.cat(idx).flatten()
+                assert len(set(j.tolist())) == 16 and torch.equal(d_all[j], rd) and torch.equal(t_all[j], tg)
+                hit = k
+        assert hit is not None
+        seen.add(hit)
+    assert seen == {0, 1}
+    with pytest.raises(ValueError):
+        while True:
+            pool.sample(49, generator=g)   # the 48-ray image cannot give 49 distinct rays (np.random.choice(replace=False) raises too)
+    ro, rd, tg = pool.sample_global(200, generator=g)
+    assert ro.shape == (200, 3)
+    val = nb.CachedValidationSet.from_dir(str(tmp_path), device="cpu")
+    h, w, f, ro, rd, tg = val.choice(generator=g)
+    assert len(val) == 1 and ro.shape == (6, 8, 3) and tg.shape == (6, 8, 4)
